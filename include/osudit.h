@@ -1,0 +1,115 @@
+/* osudit — C ABI of the B200-native DiT denoising hot path (libosudit.so).
+ *
+ * The reference (OliBomby/osu-diffusion) is pure PyTorch and has no FFI of its own,
+ * so each entry point below cites the reference Python it replaces; the host-side binding a
+ * maintainer adds is the ctypes stub in INTEGRATION.md (shipped as osu-diffusion_b200/osudit/_lib.py).
+ *
+ * Conventions (all entry points):
+ *   - return 0 on success, <0 on error; the message is in osudit_last_error() (thread-local).
+ *   - every pointer is a borrowed DEVICE pointer (the caller's allocator owns it and keeps it alive
+ *     until the work enqueued on `stream` has run); shapes/strides are explicit; `stream` is a
+ *     cudaStream_t passed as void*.
+ *   - no allocation, no host synchronisation, no mutable global state except a mutex-guarded cache
+ *     of TMA descriptors: calls are re-entrant and CUDA-graph capturable.
+ *   - bf16 tensors are row-major uint16 storage; "split-bf16" means a (hi, lo) pair with
+ *     hi = bf16(v), lo = bf16(v - hi).
+ */
+#ifndef OSUDIT_H_
+#define OSUDIT_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OSUDIT_VERSION 1
+
+int osudit_version(void);
+const char* osudit_last_error(void);
+
+/* Epilogues of osudit_gemm_bf16. */
+#define OSUDIT_EPI_F32 0       /* out fp32  = acc + bias                                  */
+#define OSUDIT_EPI_BF16 1      /* out bf16  = acc + bias                                  */
+#define OSUDIT_EPI_BF16_GELU 2 /* out bf16  = gelu_tanh(acc + bias)   (models.py:138)     */
+
+/* out[M,N] = sum_{s<nseg} A_s[M,K_s] . B_s[N,K_s]^T + bias, tcgen05/TMEM/TMA GEMM.
+ * Replaces every nn.Linear on the path: models.py:233-234 (first layer), :35-38 (t-MLP),
+ * :152-159,:193 (adaLN), :164-170 (packed QKV in_proj, out_proj), :112-119 (fc1+GELU, fc2).
+ * A_s, B_s bf16 row-major with leading dimensions lda/ldb (elements, multiple of 8); K_s % 8 == 0;
+ * N % 8 == 0; bias fp32[N] or NULL; out leading dimension ldo (elements). */
+int osudit_gemm_bf16(int nseg, const void* const* a, const int64_t* lda, const void* const* b,
+                     const int64_t* ldb, const int64_t* k, int64_t M, int64_t N, const float* bias,
+                     int epilogue, void* out, int64_t ldo, void* stream);
+
+/* Banded / full / generically masked multi-head self-attention on packed QKV.
+ * Replaces nn.MultiheadAttention's core (models.py:164-170) with the band mask of sample.py:81-84:
+ * query j attends key i iff -w_left <= i - j <= w_right (w_left = W-1, w_right = W); pass -1/-1 for
+ * no mask.  `mask` (T*T bytes, non-zero = blocked) is an optional generic mask applied on top.
+ * qkv bf16 [B*T, 3*H*head_dim], out bf16 [B*T, H*head_dim]. */
+int osudit_attn_band(const void* qkv, void* out, int B, int T, int H, int head_dim, int w_left,
+                     int w_right, const uint8_t* mask, void* stream);
+
+/* x (fp32 [rows, D], in place) += gate[b] * branch (bf16 [rows, D]) when branch != NULL, then
+ * h (bf16 [rows, D]) = LayerNorm(x) * (1 + scale[b]) + shift[b], b = row / T.
+ * gate/shift/scale point at column 0 of their chunk in the adaLN output, `mod_ld` floats per batch
+ * row.  Replaces modulate(norm(x), shift, scale) and the gated residual adds
+ * (models.py:12-13,160-163,172-174). */
+int osudit_ln_modulate(float* x, const void* branch, const float* gate, const float* shift,
+                       const float* scale, int64_t mod_ld, int64_t rows, int T, int D, void* h,
+                       void* stream);
+
+/* FinalLayer (models.py:192-196) fused with the last gated residual add and the output transpose
+ * (models.py:323-324): out fp32 [B, out_channels, T]; w fp32 [out_channels, D]. */
+int osudit_final_layer(float* x, const void* branch, const float* gate, const float* shift,
+                       const float* scale, int64_t mod_ld, int64_t rows, int T, int D,
+                       const float* w, const float* bias, int out_channels, float* out,
+                       void* stream);
+
+/* FirstLayer input (models.py:227-233, positional_embedding.py:29-77): split-bf16
+ * [sincos(x*pf_x) | sincos(y*pf_y) | sincos(o/10) | c] of shape [B*T, 384+E].
+ * x fp32 [xrows, 2, T] (row b reads x[b % xrows]: forward_with_cfg, models.py:332-333),
+ * o fp32 [B, T], c fp32 [B, E, T], freqs64 = exp(-ln(1e4) k/64). */
+int osudit_embed_xoc(const float* x, const float* o, const float* c, const float* freqs64,
+                     float pf_x, float pf_y, int B, int xrows, int T, int E, void* a_hi, void* a_lo,
+                     void* stream);
+
+/* timestep_embedding(t, 256) (positional_embedding.py:29-49) as split-bf16 [rows, 256]. */
+int osudit_timestep_features(const int64_t* t, const float* freqs128, int rows, void* hi, void* lo,
+                             void* stream);
+
+/* out[r] = SiLU(a[a_index ? a_index[r] : r] + (table ? table[y[r]] : 0)) as split-bf16 [rows, D]:
+ * the SiLU inside the t-MLP (models.py:30) and, with the label table, "SiLU(t_emb + y_emb)" in
+ * front of every adaLN Linear (models.py:73,320,148,189). */
+int osudit_silu_split(const float* a, const int32_t* a_index, const float* table, const int64_t* y,
+                      int64_t rows, int D, void* hi, void* lo, void* stream);
+
+/* fp32 -> split-bf16 (lo may be NULL): packs nn.Linear weights for the GEMM. */
+int osudit_split_bf16(const float* a, int64_t n, void* hi, void* lo, void* stream);
+
+/* One reverse-diffusion update, optionally with the classifier-free-guidance combine.
+ * Replaces models.py:338-343 + gaussian_diffusion.py:312-324,341-358,454-466.
+ * model_out fp32 [B,4,T]; x, noise, sample, pred_xstart fp32 [B,2,T]; t int64 [B] (respaced index);
+ * coef_table fp32 [K,6] = {log beta, posterior_log_variance_clipped, sqrt_recip_alphas_cumprod,
+ * sqrt_recipm1_alphas_cumprod, posterior_mean_coef1, posterior_mean_coef2}.
+ * cfg_half = B/2 to guide (eps rows b and b+B/2 combined, variance channels untouched), 0 for none.
+ * phase 0: whole step.  phase 1: only the unclamped x0 prediction into pred_xstart (the host then
+ * applies denoised_fn).  phase 2: x0 taken from x0_in, then clamp/mean/sample.
+ * sample / mean / log_variance may be NULL (p_mean_variance wants mean+log_variance, no sample). */
+int osudit_diffusion_step(const float* model_out, const float* x, const float* noise,
+                          const float* x0_in, const int64_t* t, const float* coef_table, int B, int T,
+                          int cfg_half, float cfg_scale, int clip_denoised, int phase, float* sample,
+                          float* pred_xstart, float* mean, float* log_variance, void* stream);
+
+/* forward_with_cfg's output on its own (models.py:338-343): [B,4,T] -> [B,4,T]. */
+int osudit_cfg_combine(const float* model_out, int B, int T, float cfg_scale, float* out,
+                       void* stream);
+
+/* q_sample (gaussian_diffusion.py:231-247): out = sqrt_acp[t] x0 + sqrt_1m_acp[t] noise. */
+int osudit_q_sample(const float* x0, const float* noise, const int64_t* t, const float* sqrt_acp,
+                    const float* sqrt_1m_acp, int B, int64_t per_row, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OSUDIT_H_ */

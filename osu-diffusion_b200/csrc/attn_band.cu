@@ -1,0 +1,238 @@
+// Banded multi-head self-attention over packed QKV (flash style: K/V staged in shared memory,
+// online softmax in fp32, only key tiles that intersect the band are visited).
+//
+// Reference: nn.MultiheadAttention inside DiTBlock (models.py:130-135,164-170) with the boolean
+// band mask sample.py:81-84 builds (query j may attend key i iff -(W-1) <= i-j <= W; closed form in
+// SURVEY.md F3) or no mask (training windows).  The reference computes dense TxT scores and masks
+// them; here cost is O(T * band).  A generic (T,T) byte mask is honoured per element as well.
+//
+// Layout: qkv [B*T, 3*D] bf16 (rows = tokens, [q | k | v], heads are contiguous HD-slices — the
+// packed in_proj layout), out [B*T, D] bf16.  One CTA = 64 queries of one (batch, head); 4 warps x
+// 16 query rows; mma.sync m16n8k16 bf16 with fp32 accumulation; cp.async double-buffered K/V tiles
+// in XOR-swizzled shared memory read through ldmatrix.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace osudit {
+
+constexpr int kBQ = 64;   // queries per CTA
+constexpr int kBKV = 64;  // keys per tile
+
+template <int HD>
+__device__ __forceinline__ void load_tile_async(__nv_bfloat16* s, const __nv_bfloat16* g, int64_t ld,
+                                                int row0, int T, int tid) {
+  constexpr int kChunks = HD / 8;  // 16-byte chunks per row
+  static_assert(kChunks == 8, "swizzle below assumes 128-byte rows");
+#pragma unroll
+  for (int i = 0; i < (kBKV * kChunks) / 128; ++i) {
+    const int idx = tid + i * 128;
+    const int r = idx >> 3;
+    const int ch = idx & 7;
+    const int row = row0 + r;
+    const bool valid = row >= 0 && row < T;
+    const __nv_bfloat16* src = g + static_cast<int64_t>(valid ? row : 0) * ld + ch * 8;
+    cp_async_16(reinterpret_cast<uint8_t*>(s) + r * 128 + ((ch ^ (r & 7)) << 4), src, valid);
+  }
+}
+
+template <int HD>
+__global__ void __launch_bounds__(128)
+attn_band_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int T, int H,
+                 int wl, int wr, const uint8_t* __restrict__ mask, float scale_log2) {
+  __shared__ __align__(128) __nv_bfloat16 sQ[kBQ * HD];
+  __shared__ __align__(128) __nv_bfloat16 sK[2][kBKV * HD];
+  __shared__ __align__(128) __nv_bfloat16 sV[2][kBKV * HD];
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const int q0 = blockIdx.x * kBQ;
+  const int h = blockIdx.y;
+  const int b = blockIdx.z;
+  const int D = H * HD;
+  const int64_t ld = 3 * static_cast<int64_t>(D);
+  const __nv_bfloat16* gq = qkv + static_cast<int64_t>(b) * T * ld + h * HD;
+  const __nv_bfloat16* gk = gq + D;
+  const __nv_bfloat16* gv = gq + 2 * D;
+
+  const int k_first = max(0, q0 - wl);
+  const int k_last = min(T - 1, min(q0 + kBQ - 1, T - 1) + wr);
+  const int kt_lo = k_first / kBKV;
+  const int kt_hi = k_last / kBKV;
+
+  load_tile_async<HD>(sQ, gq, ld, q0, T, tid);
+  load_tile_async<HD>(sK[0], gk, ld, kt_lo * kBKV, T, tid);
+  load_tile_async<HD>(sV[0], gv, ld, kt_lo * kBKV, T, tid);
+  cp_async_commit();
+
+  float o_acc[HD / 8][4];
+#pragma unroll
+  for (int i = 0; i < HD / 8; ++i) o_acc[i][0] = o_acc[i][1] = o_acc[i][2] = o_acc[i][3] = 0.f;
+  float m_run[2] = {-INFINITY, -INFINITY};
+  float l_run[2] = {0.f, 0.f};
+  uint32_t qf[HD / 16][4];
+
+  const int qrow[2] = {q0 + warp * 16 + (lane >> 2), q0 + warp * 16 + (lane >> 2) + 8};
+
+  for (int kt = kt_lo; kt <= kt_hi; ++kt) {
+    const int buf = (kt - kt_lo) & 1;
+    if (kt < kt_hi) {
+      load_tile_async<HD>(sK[buf ^ 1], gk, ld, (kt + 1) * kBKV, T, tid);
+      load_tile_async<HD>(sV[buf ^ 1], gv, ld, (kt + 1) * kBKV, T, tid);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+
+    if (kt == kt_lo) {
+#pragma unroll
+      for (int ks = 0; ks < HD / 16; ++ks) {
+        const int r = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+        const int ch = ks * 2 + (lane >> 4);
+        ldmatrix_x4(qf[ks], smem_u32(sQ) + r * 128 + ((ch ^ (r & 7)) << 4));
+      }
+    }
+
+    // ---- S = Q K^T (16 x 64 per warp)
+    float s[kBKV / 8][4];
+#pragma unroll
+    for (int nb = 0; nb < kBKV / 8; ++nb) s[nb][0] = s[nb][1] = s[nb][2] = s[nb][3] = 0.f;
+    const uint32_t sk = smem_u32(sK[buf]);
+#pragma unroll
+    for (int ks = 0; ks < HD / 16; ++ks) {
+#pragma unroll
+      for (int nb = 0; nb < kBKV / 8; nb += 2) {
+        uint32_t kf[4];
+        const int r = nb * 8 + (lane & 7) + ((lane >> 4) & 1) * 8;
+        const int ch = ks * 2 + ((lane >> 3) & 1);
+        ldmatrix_x4(kf, sk + r * 128 + ((ch ^ (r & 7)) << 4));
+        mma_bf16_16816(s[nb], qf[ks], kf[0], kf[1]);
+        mma_bf16_16816(s[nb + 1], qf[ks], kf[2], kf[3]);
+      }
+    }
+
+    // ---- band / tail / generic mask (skipped for tiles entirely inside the band)
+    const int k0 = kt * kBKV;
+    const bool interior = (k0 - (q0 + kBQ - 1) >= -wl) && (k0 + kBKV - 1 - q0 <= wr) &&
+                          (k0 + kBKV - 1 < T) && (mask == nullptr);
+    if (!interior) {
+#pragma unroll
+      for (int nb = 0; nb < kBKV / 8; ++nb) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int q = qrow[e >> 1];
+          const int k = k0 + nb * 8 + (lane & 3) * 2 + (e & 1);
+          bool ok = (k < T) && (k - q >= -wl) && (k - q <= wr);
+          if (ok && mask != nullptr && q < T) ok = mask[static_cast<int64_t>(q) * T + k] == 0;
+          if (!ok) s[nb][e] = -INFINITY;
+        }
+      }
+    }
+
+    // ---- online softmax (rows lane/4 and lane/4+8)
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      float mx = -INFINITY;
+#pragma unroll
+      for (int nb = 0; nb < kBKV / 8; ++nb) mx = fmaxf(mx, fmaxf(s[nb][2 * rr], s[nb][2 * rr + 1]));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      const float m_new = fmaxf(m_run[rr], mx);
+      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+      const float corr = exp2f((m_run[rr] - m_use) * scale_log2);
+      const float moff = m_use * scale_log2;
+      float sum = 0.f;
+#pragma unroll
+      for (int nb = 0; nb < kBKV / 8; ++nb) {
+        const float p0 = exp2f(s[nb][2 * rr] * scale_log2 - moff);
+        const float p1 = exp2f(s[nb][2 * rr + 1] * scale_log2 - moff);
+        s[nb][2 * rr] = p0;
+        s[nb][2 * rr + 1] = p1;
+        sum += p0 + p1;
+      }
+      l_run[rr] = l_run[rr] * corr + sum;
+      m_run[rr] = m_new;
+#pragma unroll
+      for (int db = 0; db < HD / 8; ++db) {
+        o_acc[db][2 * rr] *= corr;
+        o_acc[db][2 * rr + 1] *= corr;
+      }
+    }
+
+    // ---- O += P V
+    const uint32_t sv = smem_u32(sV[buf]);
+#pragma unroll
+    for (int kk = 0; kk < kBKV / 16; ++kk) {
+      uint32_t pf[4];
+      pf[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
+      pf[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
+      pf[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+      pf[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+      for (int db = 0; db < HD / 8; db += 2) {
+        uint32_t vf[4];
+        const int r = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+        const int ch = db + (lane >> 4);
+        ldmatrix_x4_trans(vf, sv + r * 128 + ((ch ^ (r & 7)) << 4));
+        mma_bf16_16816(o_acc[db], pf, vf[0], vf[1]);
+        mma_bf16_16816(o_acc[db + 1], pf, vf[2], vf[3]);
+      }
+    }
+    __syncthreads();  // everyone done with sK/sV[buf] before it is refilled
+  }
+
+  // ---- normalise, stage through sQ (all warps are past their Q-fragment loads), coalesced store
+#pragma unroll
+  for (int rr = 0; rr < 2; ++rr) {
+    float l = l_run[rr];
+    l += __shfl_xor_sync(0xffffffffu, l, 1);
+    l += __shfl_xor_sync(0xffffffffu, l, 2);
+    const float inv = 1.0f / l;  // 0/0 -> NaN for a fully masked row, as the reference's softmax
+    const int r = warp * 16 + (lane >> 2) + rr * 8;
+#pragma unroll
+    for (int db = 0; db < HD / 8; ++db) {
+      const uint32_t v = pack_bf16(o_acc[db][2 * rr] * inv, o_acc[db][2 * rr + 1] * inv);
+      uint8_t* dst = reinterpret_cast<uint8_t*>(sQ) + r * 128 + ((db ^ (r & 7)) << 4) + (lane & 3) * 4;
+      *reinterpret_cast<uint32_t*>(dst) = v;
+    }
+  }
+  __syncthreads();
+  __nv_bfloat16* go = out + static_cast<int64_t>(b) * T * D + h * HD;
+#pragma unroll
+  for (int i = 0; i < (kBQ * HD / 8) / 128; ++i) {
+    const int idx = tid + i * 128;
+    const int r = idx >> 3;
+    const int ch = idx & 7;
+    if (q0 + r < T) {
+      const uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<uint8_t*>(sQ) + r * 128 +
+                                                      ((ch ^ (r & 7)) << 4));
+      *reinterpret_cast<uint4*>(go + static_cast<int64_t>(q0 + r) * D + ch * 8) = v;
+    }
+  }
+}
+
+}  // namespace osudit
+
+using namespace osudit;
+
+extern "C" int osudit_attn_band(const void* qkv, void* out, int B, int T, int H, int head_dim,
+                                int w_left, int w_right, const uint8_t* mask, void* stream) {
+  if (head_dim != 64) return set_error(-1, "attn_band: only head_dim 64 is implemented");
+  if (B <= 0 || T <= 0 || H <= 0) return set_error(-1, "attn_band: bad shape");
+  if (w_left < 0 || w_left > T) w_left = T;
+  if (w_right < 0 || w_right > T) w_right = T;
+  const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(head_dim));
+  dim3 grid((T + kBQ - 1) / kBQ, H, B);
+  attn_band_kernel<64><<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), T, H, w_left,
+      w_right, mask, scale_log2);
+  OSUDIT_CHECK_LAUNCH();
+  return 0;
+}

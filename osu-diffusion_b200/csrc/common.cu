@@ -1,0 +1,33 @@
+#include "common.h"
+
+#include <string.h>
+
+#include "../../include/osudit.h"
+
+namespace osudit {
+
+static thread_local char g_err[512] = "";
+
+int set_error(int code, const char* msg) {
+  strncpy(g_err, msg ? msg : "", sizeof(g_err) - 1);
+  g_err[sizeof(g_err) - 1] = 0;
+  return code;
+}
+
+int num_sms() {
+  static int cached[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (cached[dev] == 0) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    cached[dev] = n > 0 ? n : 148;
+  }
+  return cached[dev];
+}
+
+}  // namespace osudit
+
+extern "C" const char* osudit_last_error(void) { return osudit::g_err; }
+extern "C" int osudit_version(void) { return OSUDIT_VERSION; }

@@ -1,0 +1,408 @@
+// C[M,N] = sum_s A_s[M,K_s] * B_s[N,K_s]^T (+ bias) with an activation/convert epilogue.
+//
+// The dense contractions of the DiT denoiser (reference models.py:164-170 QKV/out-proj,
+// models.py:112-119 MLP, models.py:233-234 first layer, models.py:152-159,193 adaLN,
+// models.py:35-38 t-MLP): nn.Linear stores W as [out, in], activations are [tokens, in], so
+// both operands are K-major and feed tcgen05.mma directly.
+//
+// sm_100a design (one CTA per SM, persistent over 128 x BN output tiles):
+//   warp 0      TMA producer: cp.async.bulk.tensor 2D loads, 128B-swizzled [rows][64 bf16] boxes
+//   warp 1      owns TMEM (2 accumulator stages x BN fp32 columns) and issues tcgen05.mma
+//               (M=128, N=BN, K=16, kind::f16 = bf16 in / fp32 accumulate in TMEM)
+//   warps 2..5  epilogue: tcgen05.ld 32x32b -> +bias -> (GELU-tanh) -> fp32|bf16 -> swizzled smem
+//               -> TMA store (clips the M/N tails), double-buffered against the next tile's MMAs
+// Pipelines: smem full/empty mbarriers (kStages deep), TMEM full/empty mbarriers (2 deep).
+// Up to three (A,B) K-segments are chained into one accumulator: that is how the split-bf16
+// ("bf16x3": hi*hi + lo*hi + hi*lo) first-layer / adaLN products run on the same kernel.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace osudit {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int kMaxSeg = 3;
+constexpr int kStageBytesA = BM * BK * 2;
+constexpr int kStagingBytes = BM * 128;  // one epilogue chunk: 128 rows x 128 B
+constexpr int kNumThreads = 192;
+
+struct GemmParams {
+  CUtensorMap tma_a[kMaxSeg];
+  CUtensorMap tma_b[kMaxSeg];
+  CUtensorMap tma_out;
+  int kblocks[kMaxSeg];
+  int nseg;
+  int M, N;
+  int m_tiles, n_tiles;
+  const float* bias;
+};
+
+template <int BN>
+struct Cfg {
+  static constexpr int kStageBytesB = BN * BK * 2;
+  static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
+  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kTmemCols = 2 * BN;
+  static constexpr int kBarrierBytes = 1024;
+  static constexpr int kSmemBytes =
+      kStages * kStageBytes + 2 * kStagingBytes + kBarrierBytes + 1024 /*align slack*/;
+};
+
+// UMMA shared-memory descriptor, K-major operand, SWIZZLE_128B, rows 128 B apart, 8-row groups
+// 1024 B apart (SBO); LBO is unused for swizzled K-major layouts (encoded 1); version 1 = sm_100.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+// kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, dense.
+template <int BN>
+__device__ __forceinline__ constexpr uint32_t umma_idesc() {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(BN >> 3) << 17) |
+         (static_cast<uint32_t>(BM >> 4) << 24);
+}
+
+__device__ __forceinline__ float gelu_tanh(float x) {
+  // 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3))), tanh(u) = 1 - 2 / (1 + e^{2u})
+  const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+  const float e = __expf(2.0f * u);
+  const float t = 1.0f - __fdividef(2.0f, 1.0f + e);
+  return 0.5f * x * (1.0f + t);
+}
+
+enum : int { EPI_F32 = 0, EPI_BF16 = 1, EPI_BF16_GELU = 2 };
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(kNumThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
+  using C = Cfg<BN>;
+  constexpr int kEpiCols = (EPI == EPI_F32) ? 32 : 64;  // 128 bytes of output per row per chunk
+  constexpr int kChunks = BN / kEpiCols;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* staging = smem + C::kStages * C::kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + 2 * kStagingBytes);
+  uint64_t* empty_bar = full_bar + C::kStages;
+  uint64_t* tmem_full = empty_bar + C::kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.m_tiles * p.n_tiles;
+  int total_kblocks = 0;
+  for (int s = 0; s < p.nseg; ++s) total_kblocks += p.kblocks[s];
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.nseg; ++s) {
+      tma_prefetch_desc(&p.tma_a[s]);
+      tma_prefetch_desc(&p.tma_b[s]);
+    }
+    tma_prefetch_desc(&p.tma_out);
+    for (int i = 0; i < C::kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc<C::kTmemCols>(tmem_slot);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m0 = (tile / p.n_tiles) * BM;
+        const int n0 = (tile % p.n_tiles) * BN;
+        for (int s = 0; s < p.nseg; ++s) {
+          for (int kb = 0; kb < p.kblocks[s]; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * C::kStageBytes;
+            mbar_expect_tx(&full_bar[stage], C::kStageBytes);
+            tma_load_2d(sa, &p.tma_a[s], &full_bar[stage], kb * BK, m0);
+            tma_load_2d(sa + kStageBytesA, &p.tma_b[s], &full_bar[stage], kb * BK, n0);
+            if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // -------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc<BN>();
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+        for (int kb = 0; kb < total_kblocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
+          const uint64_t da = umma_desc_sw128(sa);
+          const uint64_t db = umma_desc_sw128(sa + kStageBytesA);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in 16 B units
+            umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue
+    const int ep_tid = threadIdx.x - 64;
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may read
+    const int row = quad * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    uint32_t chunk_ctr = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m0 = (tile / p.n_tiles) * BM;
+      const int n0 = (tile % p.n_tiles) * BN;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
+                             static_cast<uint32_t>(acc * BN);
+#pragma unroll 1
+      for (int c = 0; c < kChunks; ++c, ++chunk_ctr) {
+        uint8_t* buf = staging + (chunk_ctr & 1) * kStagingBytes;
+        // the store that last read this buffer (2 chunks ago) must have drained it
+        if (ep_tid == 0) tma_store_wait_read<1>();
+        named_bar_sync(1, 128);
+        const int ncol0 = n0 + c * kEpiCols;
+        uint8_t* my_row = buf + row * 128;
+#pragma unroll
+        for (int h = 0; h < kEpiCols / 32; ++h) {
+          uint32_t r[32];
+          tmem_ld_32x32(t_row + static_cast<uint32_t>(c * kEpiCols + h * 32), r);
+          tmem_ld_wait();
+          if (c == kChunks - 1 && h == kEpiCols / 32 - 1) {
+            // accumulator fully read: hand the TMEM stage back to the MMA warp
+            tc_fence_before();
+            mbar_arrive(&tmem_empty[acc]);
+          }
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const int n = ncol0 + h * 32 + i;
+            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias != nullptr && n + 3 < p.N) b = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+            v[i + 0] = __uint_as_float(r[i + 0]) + b.x;
+            v[i + 1] = __uint_as_float(r[i + 1]) + b.y;
+            v[i + 2] = __uint_as_float(r[i + 2]) + b.z;
+            v[i + 3] = __uint_as_float(r[i + 3]) + b.w;
+          }
+          if (EPI == EPI_BF16_GELU) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = gelu_tanh(v[i]);
+          }
+          if (EPI == EPI_F32) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {  // 8 x 16 B
+              float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              *reinterpret_cast<float4*>(my_row + ((j ^ (row & 7)) << 4)) = o;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {  // 4 x 16 B (8 bf16 each) per 32 columns
+              uint4 o;
+              o.x = pack_bf16(v[8 * j + 0], v[8 * j + 1]);
+              o.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+              o.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
+              o.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+              const int jj = h * 4 + j;
+              *reinterpret_cast<uint4*>(my_row + ((jj ^ (row & 7)) << 4)) = o;
+            }
+          }
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, 128);
+        if (ep_tid == 0) {
+          tma_store_2d(&p.tma_out, buf, ncol0, m0);
+          tma_store_commit();
+        }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if (ep_tid == 0) tma_store_wait<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<C::kTmemCols>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------- host side
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) ==
+            cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  });
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr;
+  uint64_t d0, d1, stride;
+  uint32_t b0, b1, dtype;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && stride == o.stride && b0 == o.b0 &&
+           b1 == o.b1 && dtype == o.dtype;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.ptr);
+    auto mix = [&h](uint64_t v) { h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
+    mix(k.d0); mix(k.d1); mix(k.stride); mix(k.b0); mix(k.b1); mix(k.dtype);
+    return h;
+  }
+};
+
+// 2D row-major tensor [d1 rows][d0 cols], row pitch `stride_bytes`; box = [b1 rows][b0 cols],
+// 128-byte swizzle.  Descriptors depend only on the key, so a process-wide cache is safe.
+static int make_tensor_map(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1,
+                           uint64_t stride_bytes, uint32_t b0, uint32_t b1, bool is_f32) {
+  static std::mutex mu;
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  MapKey key{ptr, d0, d1, stride_bytes, b0, b1, is_f32 ? 1u : 0u};
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+      *out = it->second;
+      return 0;
+    }
+  }
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return set_error(-3, "cuTensorMapEncodeTiled entry point not available");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (stride_bytes & 15))
+    return set_error(-2, "TMA operand must be 16-byte aligned with a 16-byte-multiple row pitch");
+  cuuint64_t dims[2] = {d0, d1};
+  cuuint64_t strides[1] = {stride_bytes};
+  cuuint32_t box[2] = {b0, b1};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                   2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(-4, "cuTensorMapEncodeTiled failed");
+  std::lock_guard<std::mutex> lock(mu);
+  if (cache.size() > 65536) cache.clear();
+  cache.emplace(key, *out);
+  return 0;
+}
+
+template <int BN, int EPI>
+static int launch(const GemmParams& p, cudaStream_t stream) {
+  using C = Cfg<BN>;
+  static bool configured = false;
+  auto kern = gemm_tcgen05_kernel<BN, EPI>;
+  if (!configured) {
+    cudaError_t e =
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    if (e != cudaSuccess) return set_error(-5, cudaGetErrorString(e));
+    configured = true;
+  }
+  const int tiles = p.m_tiles * p.n_tiles;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  kern<<<grid, kNumThreads, C::kSmemBytes, stream>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(-6, cudaGetErrorString(e));
+  return 0;
+}
+
+}  // namespace osudit
+
+using namespace osudit;
+
+extern "C" int osudit_gemm_bf16(int nseg, const void* const* a, const int64_t* lda,
+                                const void* const* b, const int64_t* ldb, const int64_t* k,
+                                int64_t M, int64_t N, const float* bias, int epilogue, void* out,
+                                int64_t ldo, void* stream) {
+  if (nseg < 1 || nseg > kMaxSeg) return set_error(-1, "gemm: nseg must be 1..3");
+  if (M <= 0 || N <= 0 || (N % 8) != 0) return set_error(-1, "gemm: need M>0, N>0, N%8==0");
+  if (epilogue < 0 || epilogue > 2) return set_error(-1, "gemm: unknown epilogue");
+  const int BN = (N % 256 == 0) ? 256 : 128;
+  GemmParams p;
+  p.nseg = nseg;
+  p.M = static_cast<int>(M);
+  p.N = static_cast<int>(N);
+  p.m_tiles = static_cast<int>((M + BM - 1) / BM);
+  p.n_tiles = static_cast<int>((N + BN - 1) / BN);
+  p.bias = bias;
+  for (int s = 0; s < kMaxSeg; ++s) p.kblocks[s] = 0;
+  for (int s = 0; s < nseg; ++s) {
+    if (k[s] <= 0 || (k[s] % 8) != 0) return set_error(-1, "gemm: K must be a positive multiple of 8");
+    p.kblocks[s] = static_cast<int>((k[s] + BK - 1) / BK);
+    int rc = make_tensor_map(&p.tma_a[s], a[s], k[s], M, lda[s] * 2, BK, BM, false);
+    if (rc) return rc;
+    rc = make_tensor_map(&p.tma_b[s], b[s], k[s], N, ldb[s] * 2, BK, BN, false);
+    if (rc) return rc;
+  }
+  const bool f32 = epilogue == EPI_F32;
+  int rc = make_tensor_map(&p.tma_out, out, N, M, ldo * (f32 ? 4 : 2), f32 ? 32 : 64, BM, f32);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (BN == 256) {
+    if (epilogue == EPI_F32) return launch<256, EPI_F32>(p, st);
+    if (epilogue == EPI_BF16) return launch<256, EPI_BF16>(p, st);
+    return launch<256, EPI_BF16_GELU>(p, st);
+  }
+  if (epilogue == EPI_F32) return launch<128, EPI_F32>(p, st);
+  if (epilogue == EPI_BF16) return launch<128, EPI_BF16>(p, st);
+  return launch<128, EPI_BF16_GELU>(p, st);
+}

@@ -1,0 +1,204 @@
+"""Host-side schedule of one DiT forward over the native kernels.
+
+Mirrors DiT.forward (reference models.py:306-325) as a fixed sequence of libosudit launches on the
+current stream.  Owns (a) the packed copies of the module's fp32 parameters — bf16 for the large
+GEMMs, split-bf16 (hi, lo) for the precision-critical small ones — rebuilt when a parameter's
+version counter changes, and (b) per-shape activation workspaces, so that steady-state forwards
+allocate nothing and reuse the same TMA descriptors.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import ops
+
+FREQ_SEQ = 128  # FirstLayer.frequency_embedding_size (models.py:213)
+FREQ_T = 256  # TimestepEmbedder.frequency_embedding_size (models.py:26)
+
+
+def _freqs(half: int, device) -> torch.Tensor:
+    # positional_embedding.py:39-44, evaluated by torch on the host exactly as the reference does
+    f = torch.exp(-math.log(10000) * torch.arange(start=0, end=half, dtype=torch.float32) / half)
+    return f.to(device)
+
+
+class MaskSpec:
+    """How the attention kernel should treat `attn_mask`: band (w_left, w_right), none, or generic."""
+
+    __slots__ = ("w_left", "w_right", "generic")
+
+    def __init__(self, w_left=-1, w_right=-1, generic=None):
+        self.w_left, self.w_right, self.generic = w_left, w_right, generic
+
+
+_mask_cache: dict = {}
+
+
+def classify_mask(attn_mask, T: int) -> MaskSpec:
+    """sample.py:81-84 builds a (T,T) bool band (True = blocked).  Recognise the closed form once
+    per mask tensor so attention can skip whole key tiles; anything else is applied element-wise."""
+    if attn_mask is None:
+        return MaskSpec()
+    if attn_mask.dtype != torch.bool or attn_mask.shape != (T, T):
+        raise ValueError("attn_mask must be a (T, T) bool tensor (True = not allowed) or None")
+    key = (attn_mask.data_ptr(), attn_mask._version, T, str(attn_mask.device))
+    spec = _mask_cache.get(key)
+    if spec is not None:
+        return spec
+    allowed = ~attn_mask
+    wr = int(allowed[0].sum().item()) - 1
+    wl = int(allowed[:, 0].sum().item()) - 1
+    d = torch.arange(T, device=attn_mask.device)
+    d = d[None, :] - d[:, None]
+    if wl >= 0 and wr >= 0 and torch.equal(allowed, (d >= -wl) & (d <= wr)):
+        spec = MaskSpec(wl, wr)
+    else:
+        spec = MaskSpec(-1, -1, attn_mask.to(torch.uint8).contiguous())
+    if len(_mask_cache) > 64:
+        _mask_cache.clear()
+    _mask_cache[key] = spec
+    return spec
+
+
+class PackedWeights:
+    """GEMM-ready copies of a DiT module's parameters."""
+
+    def __init__(self, model):
+        self.versions = None
+        self.refresh(model)
+
+    @staticmethod
+    def _signature(model):
+        return tuple((p.data_ptr(), p._version) for p in model.parameters())
+
+    def refresh(self, model):
+        sig = self._signature(model)
+        if sig == self.versions:
+            return
+        bf = lambda p: p.detach().to(torch.bfloat16).contiguous()  # noqa: E731
+        f32 = lambda p: p.detach().float().contiguous()  # noqa: E731
+        self.first_w = ops.split_bf16(model.xoc_embedder.mlp[0].weight)
+        self.first_b = f32(model.xoc_embedder.mlp[0].bias)
+        self.pf = [float(v) for v in model.xoc_embedder.playfield_size.detach().cpu()]
+        self.t0_w = ops.split_bf16(model.t_embedder.mlp[0].weight)
+        self.t0_b = f32(model.t_embedder.mlp[0].bias)
+        self.t2_w = ops.split_bf16(model.t_embedder.mlp[2].weight)
+        self.t2_b = f32(model.t_embedder.mlp[2].bias)
+        self.table = f32(model.y_embedder.embedding_table.weight)
+        mods_w = [blk.adaLN_modulation[1].weight for blk in model.blocks] + \
+                 [model.final_layer.adaLN_modulation[1].weight]
+        mods_b = [blk.adaLN_modulation[1].bias for blk in model.blocks] + \
+                 [model.final_layer.adaLN_modulation[1].bias]
+        self.mod_w = ops.split_bf16(torch.cat([w.detach() for w in mods_w], 0))
+        self.mod_b = torch.cat([b.detach() for b in mods_b], 0).float().contiguous()
+        self.blocks = []
+        for blk in model.blocks:
+            self.blocks.append(dict(
+                qkv_w=bf(blk.attn.in_proj_weight), qkv_b=f32(blk.attn.in_proj_bias),
+                out_w=bf(blk.attn.out_proj.weight), out_b=f32(blk.attn.out_proj.bias),
+                fc1_w=bf(blk.mlp.fc1.weight), fc1_b=f32(blk.mlp.fc1.bias),
+                fc2_w=bf(blk.mlp.fc2.weight), fc2_b=f32(blk.mlp.fc2.bias)))
+        self.final_w = f32(model.final_layer.linear.weight)
+        self.final_b = f32(model.final_layer.linear.bias)
+        self.versions = sig
+
+
+def _gemm3(a_hi, a_lo, w, bias, out):
+    """~fp32-accurate product on the bf16 tensor cores: hi*Whi + lo*Whi + hi*Wlo."""
+    w_hi, w_lo = w
+    return ops.gemm([a_hi, a_lo, a_hi], [w_hi, w_hi, w_lo], bias, ops.EPI_F32, out)
+
+
+class DiTEngine:
+    def __init__(self, model):
+        self.model = model
+        self.D = model.hidden_size
+        self.H = model.num_heads
+        self.depth = len(model.blocks)
+        self.E = model.context_size
+        self.hidden_mlp = model.blocks[0].mlp.fc1.weight.shape[0]
+        self.weights = None
+        self._ws = {}
+        self._freqs = {}
+
+    # ------------------------------------------------------------------ helpers
+    def packed(self) -> PackedWeights:
+        if self.weights is None:
+            self.weights = PackedWeights(self.model)
+        else:
+            self.weights.refresh(self.model)
+        return self.weights
+
+    def freqs(self, half, device):
+        key = (half, str(device))
+        if key not in self._freqs:
+            self._freqs[key] = _freqs(half, device)
+        return self._freqs[key]
+
+    def workspace(self, B: int, T: int, device):
+        key = (B, T, str(device))
+        ws = self._ws.get(key)
+        if ws is None:
+            if len(self._ws) >= 4:
+                self._ws.clear()
+            rows, D = B * T, self.D
+            e = lambda *s, dt=torch.bfloat16: torch.empty(*s, dtype=dt, device=device)  # noqa: E731
+            kin = 3 * FREQ_SEQ + self.E
+            ws = dict(
+                a_hi=e(rows, kin), a_lo=e(rows, kin), x=e(rows, D, dt=torch.float32), h=e(rows, D),
+                qkv=e(rows, 3 * D), att=e(rows, D), y=e(rows, D), u=e(rows, self.hidden_mlp),
+                tf_hi=e(B, FREQ_T), tf_lo=e(B, FREQ_T), t1=e(B, D, dt=torch.float32),
+                s_hi=e(B, D), s_lo=e(B, D), temb=e(B, D, dt=torch.float32),
+                c_hi=e(B, D), c_lo=e(B, D),
+                mod=e(B, (6 * self.depth + 2) * D, dt=torch.float32),
+                out=e(B, 4, T, dt=torch.float32))
+            self._ws[key] = ws
+        return ws
+
+    # ------------------------------------------------------------------ forward
+    def conditioning(self, ws, t, y, w):
+        """mod[B, depth*6D + 2D] = every adaLN Linear applied to SiLU(t_embedder(t) + y_embedder(y))
+        (models.py:318-320,152-159,193), one batched GEMM for all blocks."""
+        dev = t.device
+        ops.timestep_features(t, self.freqs(FREQ_T // 2, dev), ws["tf_hi"], ws["tf_lo"])
+        _gemm3(ws["tf_hi"], ws["tf_lo"], w.t0_w, w.t0_b, ws["t1"])
+        ops.silu_split(ws["t1"], ws["s_hi"], ws["s_lo"])
+        _gemm3(ws["s_hi"], ws["s_lo"], w.t2_w, w.t2_b, ws["temb"])
+        ops.silu_split(ws["temb"], ws["c_hi"], ws["c_lo"], table=w.table, y=y)
+        _gemm3(ws["c_hi"], ws["c_lo"], w.mod_w, w.mod_b, ws["mod"])
+        return ws["mod"]
+
+    def forward(self, x, t, o, c, y, attn_mask=None, x_rows=None, mod=None):
+        """Returns the raw model output fp32 [B, 4, T] (a workspace tensor, overwritten by the next
+        call with the same shape).  x: [x_rows, 2, T] with x_rows in {B, B/2}."""
+        B, T = o.shape
+        D, H = self.D, self.H
+        x_rows = B if x_rows is None else x_rows
+        w = self.packed()
+        ws = self.workspace(B, T, o.device)
+        spec = classify_mask(attn_mask, T)
+
+        ops.embed_xoc(x, o, c, self.freqs(FREQ_SEQ // 2, o.device), w.pf[0], w.pf[1], x_rows,
+                      ws["a_hi"], ws["a_lo"])
+        _gemm3(ws["a_hi"], ws["a_lo"], w.first_w, w.first_b, ws["x"])
+        if mod is None:
+            mod = self.conditioning(ws, t, y, w)
+
+        xres, h, qkv, att, yb, u = ws["x"], ws["h"], ws["qkv"], ws["att"], ws["y"], ws["u"]
+        for i, bw in enumerate(w.blocks):
+            base = 6 * D * i
+            if i == 0:
+                ops.ln_modulate(xres, None, mod, 0, base, base + D, T, h)
+            else:  # fold the previous block's gated MLP residual into this LayerNorm pass
+                ops.ln_modulate(xres, yb, mod, base - D, base, base + D, T, h)
+            ops.gemm([h], [bw["qkv_w"]], bw["qkv_b"], ops.EPI_BF16, qkv)
+            ops.attn_band(qkv, att, B, T, H, D // H, spec.w_left, spec.w_right, spec.generic)
+            ops.gemm([att], [bw["out_w"]], bw["out_b"], ops.EPI_BF16, yb)
+            ops.ln_modulate(xres, yb, mod, base + 2 * D, base + 3 * D, base + 4 * D, T, h)
+            ops.gemm([h], [bw["fc1_w"]], bw["fc1_b"], ops.EPI_BF16_GELU, u)
+            ops.gemm([u], [bw["fc2_w"]], bw["fc2_b"], ops.EPI_BF16, yb)
+        fbase = 6 * D * self.depth
+        ops.final_layer(xres, yb, mod, fbase - D, fbase, fbase + D, T, w.final_w, w.final_b, ws["out"])
+        return ws["out"]

@@ -1,0 +1,169 @@
+"""Tensor-level wrappers over the C ABI: validate, pass raw pointers + the current stream.
+
+PyTorch is used for device memory and streams only; all arithmetic happens in libosudit.so.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+
+EPI_F32, EPI_BF16, EPI_BF16_GELU = 0, 1, 2
+_PTR3 = ctypes.c_void_p * 3
+_LONG3 = ctypes.c_int64 * 3
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t: torch.Tensor, dtype, name: str) -> int:
+    if not t.is_cuda:
+        raise _lib.OsuditError(f"{name}: expected a CUDA tensor (this path has no CPU fallback)")
+    if t.dtype != dtype:
+        raise _lib.OsuditError(f"{name}: expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise _lib.OsuditError(f"{name}: expected a contiguous tensor")
+    return t.data_ptr()
+
+
+def gemm(a_segs, b_segs, bias, epilogue: int, out: torch.Tensor) -> torch.Tensor:
+    """out[M,N] = sum_s a_segs[s][M,K_s] @ b_segs[s][N,K_s].T + bias (bf16 in, fp32 accumulate)."""
+    n = len(a_segs)
+    M, N = out.shape
+    ap, bp, lda, ldb, ks = _PTR3(), _PTR3(), _LONG3(), _LONG3(), _LONG3()
+    for s in range(n):
+        a, b = a_segs[s], b_segs[s]
+        if a.shape[0] != M or b.shape[0] != N or a.shape[1] != b.shape[1]:
+            raise _lib.OsuditError(f"gemm: shape mismatch {tuple(a.shape)} x {tuple(b.shape)} -> {tuple(out.shape)}")
+        ap[s] = _chk(a, torch.bfloat16, "gemm.a")
+        bp[s] = _chk(b, torch.bfloat16, "gemm.b")
+        lda[s], ldb[s], ks[s] = a.stride(0), b.stride(0), a.shape[1]
+    want = torch.float32 if epilogue == EPI_F32 else torch.bfloat16
+    op = _chk(out, want, "gemm.out")
+    bptr = _chk(bias, torch.float32, "gemm.bias") if bias is not None else None
+    lib = _lib.load()
+    _lib.check(lib.osudit_gemm_bf16(n, ap, lda, bp, ldb, ks, M, N, bptr, epilogue, op, out.stride(0),
+                                    _stream()), "osudit_gemm_bf16")
+    return out
+
+
+def attn_band(qkv, out, B, T, H, head_dim, w_left=-1, w_right=-1, mask=None):
+    mp = _chk(mask, torch.uint8, "attn.mask") if mask is not None else None
+    lib = _lib.load()
+    _lib.check(lib.osudit_attn_band(_chk(qkv, torch.bfloat16, "attn.qkv"),
+                                    _chk(out, torch.bfloat16, "attn.out"), B, T, H, head_dim,
+                                    w_left, w_right, mp, _stream()), "osudit_attn_band")
+    return out
+
+
+def _off(t: torch.Tensor, col: int) -> int:
+    return t.data_ptr() + col * t.element_size()
+
+
+def ln_modulate(x, branch, mod, gate_col, shift_col, scale_col, T, h):
+    """x fp32 [rows,D] (+= gate*branch in place), h bf16 = LN(x)*(1+scale)+shift; the three chunks
+    live at columns gate_col/shift_col/scale_col of `mod` fp32 [B, mod_ld]."""
+    rows, D = x.shape
+    _chk(mod, torch.float32, "ln.mod")
+    lib = _lib.load()
+    bp = _chk(branch, torch.bfloat16, "ln.branch") if branch is not None else None
+    gp = _off(mod, gate_col) if branch is not None else None
+    _lib.check(lib.osudit_ln_modulate(_chk(x, torch.float32, "ln.x"), bp, gp, _off(mod, shift_col),
+                                      _off(mod, scale_col), mod.stride(0), rows, T, D,
+                                      _chk(h, torch.bfloat16, "ln.h"), _stream()), "osudit_ln_modulate")
+    return h
+
+
+def final_layer(x, branch, mod, gate_col, shift_col, scale_col, T, w, bias, out):
+    rows, D = x.shape
+    _chk(mod, torch.float32, "final.mod")
+    lib = _lib.load()
+    bp = _chk(branch, torch.bfloat16, "final.branch") if branch is not None else None
+    gp = _off(mod, gate_col) if branch is not None else None
+    _lib.check(lib.osudit_final_layer(_chk(x, torch.float32, "final.x"), bp, gp, _off(mod, shift_col),
+                                      _off(mod, scale_col), mod.stride(0), rows, T, D,
+                                      _chk(w, torch.float32, "final.w"),
+                                      _chk(bias, torch.float32, "final.bias"), w.shape[0],
+                                      _chk(out, torch.float32, "final.out"), _stream()),
+               "osudit_final_layer")
+    return out
+
+
+def embed_xoc(x, o, c, freqs64, pf_x, pf_y, xrows, a_hi, a_lo):
+    B, T = o.shape
+    E = c.shape[1]
+    lib = _lib.load()
+    _lib.check(lib.osudit_embed_xoc(_chk(x, torch.float32, "embed.x"), _chk(o, torch.float32, "embed.o"),
+                                    _chk(c, torch.float32, "embed.c"),
+                                    _chk(freqs64, torch.float32, "embed.freqs"), pf_x, pf_y, B, xrows,
+                                    T, E, _chk(a_hi, torch.bfloat16, "embed.hi"),
+                                    _chk(a_lo, torch.bfloat16, "embed.lo"), _stream()), "osudit_embed_xoc")
+
+
+def timestep_features(t, freqs128, hi, lo):
+    lib = _lib.load()
+    _lib.check(lib.osudit_timestep_features(_chk(t, torch.int64, "tfeat.t"),
+                                            _chk(freqs128, torch.float32, "tfeat.freqs"), t.shape[0],
+                                            _chk(hi, torch.bfloat16, "tfeat.hi"),
+                                            _chk(lo, torch.bfloat16, "tfeat.lo"), _stream()),
+               "osudit_timestep_features")
+
+
+def silu_split(a, hi, lo, a_index=None, table=None, y=None):
+    rows, D = hi.shape
+    lib = _lib.load()
+    _lib.check(lib.osudit_silu_split(
+        _chk(a, torch.float32, "silu.a"),
+        _chk(a_index, torch.int32, "silu.index") if a_index is not None else None,
+        _chk(table, torch.float32, "silu.table") if table is not None else None,
+        _chk(y, torch.int64, "silu.y") if y is not None else None,
+        rows, D, _chk(hi, torch.bfloat16, "silu.hi"), _chk(lo, torch.bfloat16, "silu.lo"), _stream()),
+        "osudit_silu_split")
+
+
+def split_bf16(a, need_lo=True):
+    a = a.detach().contiguous()
+    hi = torch.empty(a.shape, dtype=torch.bfloat16, device=a.device)
+    lo = torch.empty_like(hi) if need_lo else None
+    lib = _lib.load()
+    _lib.check(lib.osudit_split_bf16(_chk(a, torch.float32, "split.a"), a.numel(), hi.data_ptr(),
+                                     lo.data_ptr() if need_lo else None, _stream()), "osudit_split_bf16")
+    return hi, lo
+
+
+def diffusion_step(model_out, x, noise, t, coef_table, cfg_half, cfg_scale, clip, phase, sample,
+                   pred_xstart, x0_in=None, mean=None, log_variance=None):
+    B, _, T = x.shape
+    lib = _lib.load()
+    _lib.check(lib.osudit_diffusion_step(
+        _chk(model_out, torch.float32, "step.model_out"), _chk(x, torch.float32, "step.x"),
+        _chk(noise, torch.float32, "step.noise") if noise is not None else None,
+        _chk(x0_in, torch.float32, "step.x0_in") if x0_in is not None else None,
+        _chk(t, torch.int64, "step.t"), _chk(coef_table, torch.float32, "step.coef"), B, T, cfg_half,
+        float(cfg_scale), int(bool(clip)), phase,
+        _chk(sample, torch.float32, "step.sample") if sample is not None else None,
+        _chk(pred_xstart, torch.float32, "step.pred_xstart"),
+        _chk(mean, torch.float32, "step.mean") if mean is not None else None,
+        _chk(log_variance, torch.float32, "step.log_variance") if log_variance is not None else None,
+        _stream()), "osudit_diffusion_step")
+
+
+def cfg_combine(model_out, cfg_scale, out):
+    B, _, T = model_out.shape
+    lib = _lib.load()
+    _lib.check(lib.osudit_cfg_combine(_chk(model_out, torch.float32, "cfg.in"), B, T, float(cfg_scale),
+                                      _chk(out, torch.float32, "cfg.out"), _stream()), "osudit_cfg_combine")
+    return out
+
+
+def q_sample(x0, noise, t, sqrt_acp, sqrt_1m_acp, out):
+    B = x0.shape[0]
+    lib = _lib.load()
+    _lib.check(lib.osudit_q_sample(_chk(x0, torch.float32, "q.x0"), _chk(noise, torch.float32, "q.noise"),
+                                   _chk(t, torch.int64, "q.t"), _chk(sqrt_acp, torch.float32, "q.a"),
+                                   _chk(sqrt_1m_acp, torch.float32, "q.b"), B, x0.numel() // B,
+                                   _chk(out, torch.float32, "q.out"), _stream()), "osudit_q_sample")
+    return out
