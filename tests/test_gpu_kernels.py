@@ -1,0 +1,229 @@
+"""Per-kernel parity, through the C ABI, against plain fp32 torch / the CPU oracle."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import diffusion as odiff  # noqa: E402
+from oracle import dit as odit  # noqa: E402
+from osudit import ops, synth  # noqa: E402
+
+DEV = "cuda"
+
+
+def rel(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def bf(t):
+    return t.to(torch.bfloat16)
+
+
+# ------------------------------------------------------------------------------- GEMM
+@pytest.mark.parametrize("M,N,K,epi", [
+    (128, 128, 64, ops.EPI_F32),          # one tile, one k-block
+    (128, 256, 128, ops.EPI_F32),         # BN=256 path
+    (1000, 384, 528, ops.EPI_F32),        # M tail, BN=128, K tail (528 = 8*64 + 16)
+    (2, 1536, 768, ops.EPI_F32),          # skinny M (adaLN / t-MLP shape)
+    (4096, 2304, 768, ops.EPI_BF16),      # QKV
+    (2048, 3072, 768, ops.EPI_BF16_GELU),  # fc1 + GELU
+    (2048, 768, 3072, ops.EPI_BF16),      # fc2 (long K)
+    (300 * 7, 1152, 1152, ops.EPI_BF16),  # DiT-XL width, ragged M
+    (40000, 768, 768, ops.EPI_BF16),      # > 148 tiles per CTA wave: persistent loop + TMEM double buffer
+])
+def test_gemm_single_segment(M, N, K, epi):
+    g = torch.Generator(device=DEV).manual_seed(M + N + K)
+    a = bf(torch.randn(M, K, device=DEV, generator=g))
+    w = bf(torch.randn(N, K, device=DEV, generator=g) / math.sqrt(K))
+    bias = torch.randn(N, device=DEV, generator=g)
+    ref = a.float() @ w.float().t() + bias
+    if epi == ops.EPI_F32:
+        out = ops.gemm([a], [w], bias, epi, torch.empty(M, N, device=DEV))
+        assert rel(out, ref) < 2e-6
+        assert float((out - ref).abs().max()) < 1e-4
+    else:
+        if epi == ops.EPI_BF16_GELU:
+            ref = torch.nn.functional.gelu(ref, approximate="tanh")
+        out = ops.gemm([a], [w], bias, epi, torch.empty(M, N, device=DEV, dtype=torch.bfloat16))
+        assert rel(out.float(), ref) < 3e-3          # bf16 output rounding only
+        assert torch.equal(out, bf(ref)) or float((out.float() - ref).abs().max()) < 3e-2
+
+
+def test_gemm_no_bias_and_garbage_free_tails():
+    M, N, K = 130, 136, 72
+    a = bf(torch.randn(M, K, device=DEV))
+    w = bf(torch.randn(N, K, device=DEV))
+    canvas = torch.full((M + 8, N), 7.0, device=DEV)
+    out = ops.gemm([a], [w], None, ops.EPI_F32, canvas[:M])
+    assert rel(out, a.float() @ w.float().t()) < 2e-6
+    assert bool((canvas[M:] == 7.0).all())  # TMA store clipped at M
+
+
+def test_gemm_split_bf16_three_segments_is_fp32_accurate():
+    """hi*Whi + lo*Whi + hi*Wlo: the first-layer / adaLN precision policy."""
+    M, N, K = 512, 768, 528
+    a = torch.randn(M, K, device=DEV)
+    w = torch.randn(N, K, device=DEV) * 0.02
+    bias = torch.randn(N, device=DEV) * 0.1
+    a_hi, a_lo = ops.split_bf16(a)
+    w_hi, w_lo = ops.split_bf16(w)
+    assert float((a_hi.float() + a_lo.float() - a).abs().max()) < 4e-5 * float(a.abs().max())
+    out = ops.gemm([a_hi, a_lo, a_hi], [w_hi, w_hi, w_lo], bias, ops.EPI_F32, torch.empty(M, N, device=DEV))
+    ref = (a.double() @ w.double().t() + bias.double()).float()
+    one = ops.gemm([a_hi], [w_hi], bias, ops.EPI_F32, torch.empty(M, N, device=DEV))
+    assert rel(out, ref) < 5e-5
+    assert rel(one, ref) > 20 * rel(out, ref)  # the split really buys precision
+
+
+# -------------------------------------------------------------------------- attention
+def _attn_ref(qkv, B, T, H, hd, mask):
+    D = H * hd
+    q, k, v = (z.reshape(B, T, H, hd).transpose(1, 2).float() for z in qkv.reshape(B, T, 3 * D).split(D, -1))
+    s = q @ k.transpose(-1, -2) / math.sqrt(hd)
+    if mask is not None:
+        s = s.masked_fill(mask, float("-inf"))
+    return (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B * T, D)
+
+
+@pytest.mark.parametrize("B,T,H,W", [(2, 300, 3, 128), (1, 512, 2, 8), (3, 64, 1, 128), (2, 2048, 2, 128),
+                                     (2, 130, 2, None)])
+def test_attn_band(B, T, H, W):
+    hd = 64
+    qkv = bf(torch.randn(B * T, 3 * H * hd, device=DEV))
+    out = torch.empty(B * T, H * hd, device=DEV, dtype=torch.bfloat16)
+    if W is None:
+        ops.attn_band(qkv, out, B, T, H, hd)
+        ref = _attn_ref(qkv, B, T, H, hd, None)
+    else:
+        ops.attn_band(qkv, out, B, T, H, hd, W - 1, W)
+        ref = _attn_ref(qkv, B, T, H, hd, synth.band_mask(T, W).to(DEV))
+    assert rel(out.float(), ref) < 6e-3
+    assert float((out.float() - ref).abs().max()) < 5e-2
+
+
+def test_attn_generic_mask():
+    B, T, H, hd = 2, 200, 2, 64
+    qkv = bf(torch.randn(B * T, 3 * H * hd, device=DEV))
+    mask = torch.rand(T, T, device=DEV) < 0.5
+    mask.fill_diagonal_(False)
+    out = torch.empty(B * T, H * hd, device=DEV, dtype=torch.bfloat16)
+    ops.attn_band(qkv, out, B, T, H, hd, -1, -1, mask.to(torch.uint8).contiguous())
+    assert rel(out.float(), _attn_ref(qkv, B, T, H, hd, mask)) < 6e-3
+
+
+# ---------------------------------------------------------------- LayerNorm / final layer
+@pytest.mark.parametrize("D", [384, 768, 1024, 1152])
+@pytest.mark.parametrize("branch", [False, True])
+def test_ln_modulate(D, branch):
+    B, T = 3, 101
+    rows = B * T
+    x = torch.randn(rows, D, device=DEV) * 2 + 0.5
+    mod = torch.randn(B, 6 * D, device=DEV) * 0.3
+    y = bf(torch.randn(rows, D, device=DEV)) if branch else None
+    x_ref = x.clone()
+    if branch:
+        x_ref = x_ref + mod[:, 2 * D:3 * D].repeat_interleave(T, 0) * y.float()
+    ln = torch.nn.functional.layer_norm(x_ref, (D,), eps=1e-6)
+    h_ref = ln * (1 + mod[:, D:2 * D].repeat_interleave(T, 0)) + mod[:, :D].repeat_interleave(T, 0)
+    h = torch.empty(rows, D, device=DEV, dtype=torch.bfloat16)
+    ops.ln_modulate(x, y, mod, 2 * D, 0, D, T, h)
+    assert rel(x, x_ref) < 1e-6
+    assert rel(h.float(), h_ref) < 3e-3
+    assert float((h.float() - bf(h_ref).float()).abs().max()) < 4e-2
+
+
+@pytest.mark.parametrize("D", [384, 768, 1152])
+def test_final_layer(D):
+    B, T = 2, 77
+    rows = B * T
+    x = torch.randn(rows, D, device=DEV)
+    y = bf(torch.randn(rows, D, device=DEV))
+    mod = torch.randn(B, 8 * D, device=DEV) * 0.3
+    w = torch.randn(4, D, device=DEV) * 0.05
+    bias = torch.randn(4, device=DEV)
+    xr = x + mod[:, 5 * D:6 * D].repeat_interleave(T, 0) * y.float()
+    hn = torch.nn.functional.layer_norm(xr, (D,), eps=1e-6)
+    hn = hn * (1 + mod[:, 7 * D:].repeat_interleave(T, 0)) + mod[:, 6 * D:7 * D].repeat_interleave(T, 0)
+    ref = (hn @ w.t() + bias).reshape(B, T, 4).transpose(1, 2)
+    out = torch.empty(B, 4, T, device=DEV)
+    ops.final_layer(x, y, mod, 5 * D, 6 * D, 7 * D, T, w, bias, out)
+    assert rel(out, ref) < 2e-5
+
+
+# ------------------------------------------------------------------------- embeddings
+def test_embed_xoc_matches_oracle():
+    n, T = 2, 100
+    z, o, c, y = synth.sampling_batch(n, T, seed=3)
+    o = o + 250000.0  # 25 000 rad arguments: needs accurate range reduction
+    sd = {"xoc_embedder.playfield_size": torch.tensor((512.0, 384.0))}
+    ref = odit.first_layer_input(sd, torch.cat([z[:n], z[:n]]).transpose(1, 2), o, c.transpose(1, 2))
+    B = 2 * n
+    hi = torch.empty(B * T, 528, device=DEV, dtype=torch.bfloat16)
+    lo = torch.empty_like(hi)
+    freqs = torch.exp(-math.log(10000) * torch.arange(64, dtype=torch.float32) / 64).to(DEV)
+    ops.embed_xoc(z.to(DEV), o.to(DEV), c.to(DEV), freqs, 512.0, 384.0, n, hi, lo)
+    got = (hi.float() + lo.float()).cpu().reshape(B, T, 528)
+    assert float((got - ref).abs().max()) < 2e-5
+    assert rel(hi.float().cpu().reshape(B, T, 528), ref) < 3e-3
+
+
+def test_timestep_features_and_silu_split():
+    t = torch.tensor([0, 10, 505, 999], device=DEV)
+    freqs = torch.exp(-math.log(10000) * torch.arange(128, dtype=torch.float32) / 128).to(DEV)
+    hi = torch.empty(4, 256, device=DEV, dtype=torch.bfloat16)
+    lo = torch.empty_like(hi)
+    ops.timestep_features(t, freqs, hi, lo)
+    ref = odit.sincos(t.cpu(), 256)
+    assert float(((hi.float() + lo.float()).cpu() - ref).abs().max()) < 1e-5
+    a = torch.randn(3, 384, device=DEV) * 3
+    table = torch.randn(11, 384, device=DEV)
+    yy = torch.tensor([10, 0, 3], device=DEV)
+    idx = torch.tensor([2, 2, 0], device=DEV, dtype=torch.int32)
+    h2 = torch.empty(3, 384, device=DEV, dtype=torch.bfloat16)
+    l2 = torch.empty_like(h2)
+    ops.silu_split(a, h2, l2, a_index=idx, table=table, y=yy)
+    ref2 = torch.nn.functional.silu(a[idx.long()] + table[yy])
+    assert float((h2.float() + l2.float() - ref2).abs().max()) < 5e-5
+
+
+# ---------------------------------------------------------------------- diffusion step
+@pytest.mark.parametrize("cfg", [False, True])
+def test_diffusion_step_matches_oracle(cfg):
+    s = odiff.Schedule("100")
+    B, T = 6, 333
+    g = torch.Generator().manual_seed(5)
+    out_m = torch.randn(B, 4, T, generator=g)
+    x = torch.randn(B, 2, T, generator=g)
+    noise = torch.randn(B, 2, T, generator=g)
+    t = torch.tensor([99, 98, 50, 1, 0, 0])
+    import numpy as np
+    table = torch.from_numpy(np.stack([s.log_betas, s.posterior_log_variance_clipped,
+                                       s.sqrt_recip_alphas_cumprod, s.sqrt_recipm1_alphas_cumprod,
+                                       s.posterior_mean_coef1, s.posterior_mean_coef2], 1)).float().to(DEV)
+    m_in = out_m
+    if cfg:
+        eps, rest = out_m[:, :2], out_m[:, 2:]
+        c_, u_ = eps.split(B // 2)
+        ge = u_ + 1.5 * (c_ - u_)
+        m_in = torch.cat([torch.cat([ge, ge]), rest], 1)
+    ref = odiff.p_sample(s, m_in, x, t, noise)
+    sample = torch.empty(B, 2, T, device=DEV)
+    x0 = torch.empty_like(sample)
+    ops.diffusion_step(out_m.to(DEV), x.to(DEV), noise.to(DEV), t.to(DEV), table, B // 2 if cfg else 0,
+                       1.5, True, 0, sample, x0)
+    torch.testing.assert_close(x0.cpu(), ref["pred_xstart"], rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(sample.cpu(), ref["sample"], rtol=2e-6, atol=2e-6)
+    # two-phase variant around a host callback (applied before the clamp)
+    keep = torch.rand(B, 2, T, generator=g) < 0.3
+    fn = lambda v: torch.where(keep.to(v.device), torch.full_like(v, 0.25), v)  # noqa: E731
+    ref2 = odiff.p_sample(s, m_in, x, t, noise, denoised_fn=fn)
+    ops.diffusion_step(out_m.to(DEV), x.to(DEV), None, t.to(DEV), table, B // 2 if cfg else 0, 1.5, True,
+                       1, None, x0)
+    x0_cb = fn(x0).contiguous()
+    ops.diffusion_step(out_m.to(DEV), x.to(DEV), noise.to(DEV), t.to(DEV), table, B // 2 if cfg else 0,
+                       1.5, True, 2, sample, x0, x0_in=x0_cb)
+    torch.testing.assert_close(sample.cpu(), ref2["sample"], rtol=2e-6, atol=2e-6)
+    torch.testing.assert_close(x0.cpu(), ref2["pred_xstart"], rtol=1e-6, atol=1e-6)

@@ -1,0 +1,144 @@
+"""CPU-side checks: the C-ABI library loads and exports what include/osudit.h declares, the
+drop-in modules keep the reference's surface (names, shapes, order, schedules), and the product
+path refuses to run without CUDA instead of falling back."""
+import ctypes
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from osudit import _lib
+    with open(os.path.join(ROOT, "include", "osudit.h")) as f:
+        declared = set(re.findall(r"\b(osudit_\w+)\s*\(", f.read()))
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert _lib.load().osudit_version() == 1
+
+
+def test_no_reference_or_oracle_imports_in_product():
+    """The product path must not route through the oracle or read /root/reference."""
+    pkg = os.path.join(ROOT, "osu-diffusion_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, fn)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), fn
+                assert "sys.path" not in src or "reference" not in src, fn
+
+
+@pytest.mark.parametrize("name", ["DiT-S", "DiT-B", "DiT-L", "DiT-XL"])
+def test_parameter_tree_matches_reference(golden_dir, name):
+    import models
+    with open(os.path.join(golden_dir, "registry_layout.json")) as f:
+        layout = json.load(f)
+    with torch.device("meta"):
+        m = models.DiT_models[name](num_classes=52670, context_size=144)
+    assert [[k, list(v.shape)] for k, v in m.state_dict().items()] == layout[name]
+    assert [k for k, _ in m.named_parameters()] == layout[name + ".param_order"]
+    assert m.num_heads == layout[name + ".num_heads"]
+    assert [k for k, p in m.named_parameters() if not p.requires_grad] == ["xoc_embedder.playfield_size"]
+
+
+def test_constructor_kwargs_and_init_statistics():
+    import models
+    torch.manual_seed(0)
+    m = models.DiT(hidden_size=128, depth=2, num_heads=2, num_classes=10, context_size=144,
+                   class_dropout_prob=0.2)
+    sd = m.state_dict()
+    assert sd["y_embedder.embedding_table.weight"].shape == (11, 128)
+    for k, v in sd.items():
+        if "adaLN_modulation" in k or k.startswith("final_layer.linear"):
+            assert float(v.abs().max()) == 0.0, k  # zero-init (reference models.py:295-304)
+        elif k.endswith("bias"):
+            assert float(v.abs().max()) == 0.0, k
+    assert abs(float(sd["xoc_embedder.mlp.0.weight"].std()) - 0.02) < 2e-3
+    bound = (6.0 / (128 + 384)) ** 0.5
+    assert float(sd["blocks.0.attn.in_proj_weight"].abs().max()) <= bound
+    m2 = models.DiT(hidden_size=128, depth=1, num_heads=2, num_classes=10, class_dropout_prob=0.0)
+    assert m2.state_dict()["y_embedder.embedding_table.weight"].shape == (10, 128)
+    import copy
+    m3 = copy.deepcopy(m)  # EMA copy (train.py:147)
+    assert m3._engine is None and list(m3.state_dict()) == list(sd)
+
+
+def test_cpu_call_fails_loudly():
+    import models
+    from osudit import synth
+    m = models.DiT(hidden_size=128, depth=1, num_heads=2, num_classes=10, context_size=144).eval()
+    z, o, c, y = synth.sampling_batch(1, 32, seed=0, num_classes=10)
+    with pytest.raises(RuntimeError, match="no CPU fallback"), torch.no_grad():
+        m(z, torch.tensor([0, 0]), o=o, c=c, y=y)
+    with pytest.raises(RuntimeError, match="no CPU fallback"), torch.no_grad():
+        m.forward_with_cfg(z, torch.tensor([0, 0]), o=o, c=c, y=y, cfg_scale=2.0)
+
+
+@pytest.mark.parametrize("tag,resp,sched", [
+    ("c100", "100", "squaredcos_cap_v2"), ("c250", "250", "squaredcos_cap_v2"),
+    ("c1000", "", "squaredcos_cap_v2"), ("l50", "50", "linear"), ("c10_20", "10,20", "squaredcos_cap_v2")])
+def test_create_diffusion_tables_bit_exact(golden_dir, tag, resp, sched):
+    from diffusion import create_diffusion
+    z = np.load(os.path.join(golden_dir, "schedule.npz"))
+    d = create_diffusion(resp, noise_schedule=sched)
+    assert list(z[tag + ".timestep_map"]) == d.timestep_map
+    assert d.num_timesteps == len(d.timestep_map)
+    for name in ("betas", "alphas_cumprod", "sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod",
+                 "posterior_log_variance_clipped", "posterior_mean_coef1", "posterior_mean_coef2",
+                 "sqrt_alphas_cumprod", "sqrt_one_minus_alphas_cumprod", "posterior_variance"):
+        np.testing.assert_array_equal(z[f"{tag}.{name}"], getattr(d, name), err_msg=name)
+
+
+def test_create_diffusion_surface():
+    from diffusion import create_diffusion, gaussian_diffusion as gd, space_timesteps
+    d = create_diffusion("", noise_schedule="squaredcos_cap_v2", use_l1=True)
+    assert d.loss_type == gd.LossType.L1 and d.model_var_type == gd.ModelVarType.LEARNED_RANGE
+    assert d.model_mean_type == gd.ModelMeanType.EPSILON and d.original_num_steps == 1000
+    assert create_diffusion("").loss_type == gd.LossType.MSE
+    assert sorted(space_timesteps(1000, "ddim50"))[:3] == [0, 20, 40]
+    assert sorted(space_timesteps(300, [10, 15, 20]))[:3] == [0, 11, 22]
+    with pytest.raises(ValueError):
+        space_timesteps(10, "20")
+    for name in ("p_sample", "p_sample_loop", "p_sample_loop_progressive", "training_losses",
+                 "q_sample", "p_mean_variance"):
+        assert callable(getattr(d, name))
+
+
+def test_mask_classification_closed_form():
+    from osudit import synth
+    from osudit.engine import classify_mask
+    T = 300
+    loop = torch.full((T, T), True)
+    for i in range(T):  # the reference's loop, sample.py:81-84
+        loop[max(0, i - 128): min(T, i + 128), i] = False
+    spec = classify_mask(loop, T)
+    assert (spec.w_left, spec.w_right, spec.generic) == (127, 128, None)
+    assert torch.equal(loop, synth.band_mask(T, 128))
+    none = classify_mask(None, T)
+    assert (none.w_left, none.w_right, none.generic) == (-1, -1, None)
+    weird = loop.clone()
+    weird[0, T - 1] = False
+    g = classify_mask(weird, T)
+    assert g.generic is not None and g.generic.dtype == torch.uint8
+    full = classify_mask(torch.zeros(T, T, dtype=torch.bool), T)
+    assert full.generic is None and full.w_left == T - 1 and full.w_right == T - 1
+    with pytest.raises(ValueError):
+        classify_mask(torch.zeros(T, T), T)
+
+
+def test_synthetic_inputs_shape_and_layout():
+    from osudit import synth
+    z, o, c, y = synth.sampling_batch(3, 64, seed=1)
+    assert z.shape == (6, 2, 64) and o.shape == (6, 64) and c.shape == (6, 144, 64) and y.shape == (6,)
+    assert torch.equal(z[:3], z[3:]) and torch.equal(c[:3], c[3:]) and bool((y[3:] == 52670).all())
+    assert bool((o[:, 0] == 0).all()) and bool((o[:, 1:] > o[:, :-1]).all())
+    assert bool((c[:, 128:].sum(1) == 1).all())  # one-hot datapoint type
+    (x, o2, c2), y2 = synth.training_batch(4, 128, seed=0)
+    assert x.shape == (4, 2, 128) and float(x.min()) >= 0 and float(x.max()) <= 1 and y2.shape == (4,)
