@@ -15,7 +15,12 @@ _PTR3 = ctypes.c_void_p * 3
 _LONG3 = ctypes.c_int64 * 3
 
 
+launch_count = 0  # native kernel launches issued through this module (bench.py reports it)
+
+
 def _stream() -> int:
+    global launch_count
+    launch_count += 1
     return torch.cuda.current_stream().cuda_stream
 
 
