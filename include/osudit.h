@@ -46,9 +46,15 @@ int osudit_gemm_bf16(int nseg, const void* const* a, const int64_t* lda, const v
  * Replaces nn.MultiheadAttention's core (models.py:164-170) with the band mask of sample.py:81-84:
  * query j attends key i iff -w_left <= i - j <= w_right (w_left = W-1, w_right = W); pass -1/-1 for
  * no mask.  `mask` (T*T bytes, non-zero = blocked) is an optional generic mask applied on top.
- * qkv bf16 [B*T, 3*H*head_dim], out bf16 [B*T, H*head_dim]. */
+ * qkv bf16 [B*T, 3*H*head_dim], out bf16 [B*T, H*head_dim].
+ * algo: AUTO picks the tcgen05 window kernel (128 queries x 384-key window, S and O in TMEM) when
+ * the allowed keys of every 128-query tile fit its window (band within +-128, or T <= 256; no
+ * generic mask), else the mma.sync flash kernel; the other two values force one (tests). */
+#define OSUDIT_ATTN_AUTO 0
+#define OSUDIT_ATTN_MMA_SYNC 1
+#define OSUDIT_ATTN_TCGEN05 2
 int osudit_attn_band(const void* qkv, void* out, int B, int T, int H, int head_dim, int w_left,
-                     int w_right, const uint8_t* mask, void* stream);
+                     int w_right, const uint8_t* mask, int algo, void* stream);
 
 /* x (fp32 [rows, D], in place) += gate[b] * branch (bf16 [rows, D]) when branch != NULL, then
  * h (bf16 [rows, D]) = LayerNorm(x) * (1 + scale[b]) + shift[b], b = row / T.

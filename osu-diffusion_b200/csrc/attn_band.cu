@@ -15,6 +15,7 @@
 #include <math.h>
 #include <stdint.h>
 
+#include "../../include/osudit.h"
 #include "common.h"
 #include "ptx.cuh"
 
@@ -218,16 +219,26 @@ attn_band_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
   }
 }
 
+bool attn_window_applicable(int T, int head_dim, int w_left, int w_right, const uint8_t* mask);
+int attn_window_launch(const void* qkv, void* out, int B, int T, int H, int w_left, int w_right,
+                       cudaStream_t stream);
+
 }  // namespace osudit
 
 using namespace osudit;
 
 extern "C" int osudit_attn_band(const void* qkv, void* out, int B, int T, int H, int head_dim,
-                                int w_left, int w_right, const uint8_t* mask, void* stream) {
+                                int w_left, int w_right, const uint8_t* mask, int algo, void* stream) {
   if (head_dim != 64) return set_error(-1, "attn_band: only head_dim 64 is implemented");
   if (B <= 0 || T <= 0 || H <= 0) return set_error(-1, "attn_band: bad shape");
   if (w_left < 0 || w_left > T) w_left = T;
   if (w_right < 0 || w_right > T) w_right = T;
+  const bool window_ok = attn_window_applicable(T, head_dim, w_left, w_right, mask);
+  if (algo == OSUDIT_ATTN_TCGEN05 && !window_ok)
+    return set_error(-1, "attn_band: tcgen05 window kernel needs head_dim 64, no generic mask, and "
+                         "a band within +-128 or T <= 256");
+  if (algo != OSUDIT_ATTN_MMA_SYNC && window_ok)
+    return attn_window_launch(qkv, out, B, T, H, w_left, w_right, static_cast<cudaStream_t>(stream));
   const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(head_dim));
   dim3 grid((T + kBQ - 1) / kBQ, H, B);
   attn_band_kernel<64><<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(

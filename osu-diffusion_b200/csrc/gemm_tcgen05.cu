@@ -296,29 +296,31 @@ static EncodeTiledFn get_encode_fn() {
 
 struct MapKey {
   const void* ptr;
-  uint64_t d0, d1, stride;
+  uint64_t d0, d1, d2, stride1, stride2;
   uint32_t b0, b1, dtype;
   bool operator==(const MapKey& o) const {
-    return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && stride == o.stride && b0 == o.b0 &&
-           b1 == o.b1 && dtype == o.dtype;
+    return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && stride1 == o.stride1 &&
+           stride2 == o.stride2 && b0 == o.b0 && b1 == o.b1 && dtype == o.dtype;
   }
 };
 struct MapKeyHash {
   size_t operator()(const MapKey& k) const {
     size_t h = reinterpret_cast<size_t>(k.ptr);
     auto mix = [&h](uint64_t v) { h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
-    mix(k.d0); mix(k.d1); mix(k.stride); mix(k.b0); mix(k.b1); mix(k.dtype);
+    mix(k.d0); mix(k.d1); mix(k.d2); mix(k.stride1); mix(k.stride2); mix(k.b0); mix(k.b1); mix(k.dtype);
     return h;
   }
 };
 
-// 2D row-major tensor [d1 rows][d0 cols], row pitch `stride_bytes`; box = [b1 rows][b0 cols],
-// 128-byte swizzle.  Descriptors depend only on the key, so a process-wide cache is safe.
-static int make_tensor_map(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1,
-                           uint64_t stride_bytes, uint32_t b0, uint32_t b1, bool is_f32) {
+// Row-major tensor [d2][d1 rows][d0 cols] (d2 == 0: plain 2-D), row pitch `stride1_bytes`, plane
+// pitch `stride2_bytes`; box = [1][b1 rows][b0 cols], 128-byte swizzle, zero fill out of bounds.
+// Descriptors depend only on the key, so a process-wide cache is safe.
+static int make_tensor_map_nd(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2,
+                              uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t b0, uint32_t b1,
+                              bool is_f32) {
   static std::mutex mu;
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
-  MapKey key{ptr, d0, d1, stride_bytes, b0, b1, is_f32 ? 1u : 0u};
+  MapKey key{ptr, d0, d1, d2, stride1_bytes, stride2_bytes, b0, b1, is_f32 ? 1u : 0u};
   {
     std::lock_guard<std::mutex> lock(mu);
     auto it = cache.find(key);
@@ -329,14 +331,15 @@ static int make_tensor_map(CUtensorMap* out, const void* ptr, uint64_t d0, uint6
   }
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return set_error(-3, "cuTensorMapEncodeTiled entry point not available");
-  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (stride_bytes & 15))
-    return set_error(-2, "TMA operand must be 16-byte aligned with a 16-byte-multiple row pitch");
-  cuuint64_t dims[2] = {d0, d1};
-  cuuint64_t strides[1] = {stride_bytes};
-  cuuint32_t box[2] = {b0, b1};
-  cuuint32_t estr[2] = {1, 1};
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (stride1_bytes & 15) || (stride2_bytes & 15))
+    return set_error(-2, "TMA operand must be 16-byte aligned with 16-byte-multiple pitches");
+  const cuuint32_t rank = d2 ? 3 : 2;
+  cuuint64_t dims[3] = {d0, d1, d2 ? d2 : 1};
+  cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
+  cuuint32_t box[3] = {b0, b1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(out, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
-                   2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   rank, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(-4, "cuTensorMapEncodeTiled failed");
@@ -344,6 +347,16 @@ static int make_tensor_map(CUtensorMap* out, const void* ptr, uint64_t d0, uint6
   if (cache.size() > 65536) cache.clear();
   cache.emplace(key, *out);
   return 0;
+}
+
+static int make_tensor_map(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1,
+                           uint64_t stride_bytes, uint32_t b0, uint32_t b1, bool is_f32) {
+  return make_tensor_map_nd(out, ptr, d0, d1, 0, stride_bytes, 0, b0, b1, is_f32);
+}
+
+int make_tensor_map_3d(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2,
+                       uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t b0, uint32_t b1) {
+  return make_tensor_map_nd(out, ptr, d0, d1, d2, stride1_bytes, stride2_bytes, b0, b1, false);
 }
 
 template <int BN, int EPI>

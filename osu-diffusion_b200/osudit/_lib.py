@@ -22,7 +22,7 @@ SIGNATURES = {
     "osudit_version": [],
     "osudit_last_error": [],
     "osudit_gemm_bf16": [_I, _P, _P, _P, _P, _P, _L, _L, _P, _I, _P, _L, _P],
-    "osudit_attn_band": [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P],
+    "osudit_attn_band": [_P, _P, _I, _I, _I, _I, _I, _I, _P, _I, _P],
     "osudit_ln_modulate": [_P, _P, _P, _P, _P, _L, _L, _I, _I, _P, _P],
     "osudit_final_layer": [_P, _P, _P, _P, _P, _L, _L, _I, _I, _P, _P, _I, _P, _P],
     "osudit_embed_xoc": [_P, _P, _P, _P, _F, _F, _I, _I, _I, _I, _P, _P, _P],

@@ -55,12 +55,15 @@ def gemm(a_segs, b_segs, bias, epilogue: int, out: torch.Tensor) -> torch.Tensor
     return out
 
 
-def attn_band(qkv, out, B, T, H, head_dim, w_left=-1, w_right=-1, mask=None):
+ATTN_AUTO, ATTN_MMA_SYNC, ATTN_TCGEN05 = 0, 1, 2
+
+
+def attn_band(qkv, out, B, T, H, head_dim, w_left=-1, w_right=-1, mask=None, algo=ATTN_AUTO):
     mp = _chk(mask, torch.uint8, "attn.mask") if mask is not None else None
     lib = _lib.load()
     _lib.check(lib.osudit_attn_band(_chk(qkv, torch.bfloat16, "attn.qkv"),
                                     _chk(out, torch.bfloat16, "attn.out"), B, T, H, head_dim,
-                                    w_left, w_right, mp, _stream()), "osudit_attn_band")
+                                    w_left, w_right, mp, algo, _stream()), "osudit_attn_band")
     return out
 
 

@@ -88,20 +88,37 @@ def _attn_ref(qkv, B, T, H, hd, mask):
     return (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B * T, D)
 
 
+@pytest.mark.parametrize("algo", [ops.ATTN_MMA_SYNC, ops.ATTN_TCGEN05])
 @pytest.mark.parametrize("B,T,H,W", [(2, 300, 3, 128), (1, 512, 2, 8), (3, 64, 1, 128), (2, 2048, 2, 128),
-                                     (2, 130, 2, None)])
-def test_attn_band(B, T, H, W):
+                                     (2, 130, 2, None), (4, 128, 3, None), (1, 256, 1, None), (2, 1000, 2, 100),
+                                     (1, 129, 1, 128)])
+def test_attn_band(B, T, H, W, algo):
     hd = 64
-    qkv = bf(torch.randn(B * T, 3 * H * hd, device=DEV))
-    out = torch.empty(B * T, H * hd, device=DEV, dtype=torch.bfloat16)
+    g = torch.Generator(device=DEV).manual_seed(B * 1000 + T)
+    qkv = bf(torch.randn(B * T, 3 * H * hd, device=DEV, generator=g) * 1.5)
+    out = torch.full((B * T, H * hd), float("nan"), device=DEV, dtype=torch.bfloat16)
     if W is None:
-        ops.attn_band(qkv, out, B, T, H, hd)
+        ops.attn_band(qkv, out, B, T, H, hd, algo=algo)
         ref = _attn_ref(qkv, B, T, H, hd, None)
     else:
-        ops.attn_band(qkv, out, B, T, H, hd, W - 1, W)
+        ops.attn_band(qkv, out, B, T, H, hd, W - 1, W, algo=algo)
         ref = _attn_ref(qkv, B, T, H, hd, synth.band_mask(T, W).to(DEV))
+    assert not bool(torch.isnan(out.float()).any())
     assert rel(out.float(), ref) < 6e-3
     assert float((out.float() - ref).abs().max()) < 5e-2
+
+
+def test_attn_window_kernel_rejects_what_it_cannot_do():
+    from osudit import _lib
+    qkv = bf(torch.randn(2 * 512, 3 * 64, device=DEV))
+    out = torch.empty(2 * 512, 64, device=DEV, dtype=torch.bfloat16)
+    with pytest.raises(_lib.OsuditError):
+        ops.attn_band(qkv, out, 2, 512, 1, 64, algo=ops.ATTN_TCGEN05)           # full attention, T > 256
+    with pytest.raises(_lib.OsuditError):
+        ops.attn_band(qkv, out, 2, 512, 1, 64, 199, 200, algo=ops.ATTN_TCGEN05)  # band wider than the window
+    ops.attn_band(qkv, out, 2, 512, 1, 64, 199, 200)                            # AUTO falls back to mma.sync
+    ref = _attn_ref(qkv, 2, 512, 1, 64, synth.band_mask(512, 200).to(DEV))
+    assert rel(out.float(), ref) < 6e-3
 
 
 def test_attn_generic_mask():
