@@ -13,9 +13,13 @@
 //   warp 1   tcgen05.mma issuer: S[128x384] = Q K^T into TMEM (3 x N=128, K=64), later
 //            O[128x64] = P V (24 x K=16; V is consumed as an MN-major B operand straight from the
 //            [key][dim] tile, P as a K-major A operand from shared memory)
-//   warps 2-5 one thread per query row: tcgen05.ld the S row, band/tail mask, max, exp2, sum — all
+//   warps 2-5 one thread per query row: tcgen05.ld the S row ONCE (pipelined 32-column chunks),
+//            band/tail mask, exp2 against a lazily updated power-of-two reference, sum — all
 //            thread-local, no shuffles — write P as bf16 into the swizzled A-operand layout, then
-//            normalise O and store it
+//            normalise O and store it.  (TMEM->register bandwidth, ~64 B/clk/SM, and MUFU exp2
+//            bound this kernel for head_dim 64, so S must not be read twice.)
+// Software pipeline: the MMA warp issues S(i+1) slab by slab while tile i is exponentiated (each
+// 128-column slab of S is released as soon as it has been read), then PV(i).
 // TMEM: 384 columns of S + 64 of O.  Shared memory: Q 16K + K 48K + V 48K + P 96K.
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -42,9 +46,11 @@ constexpr int kSmemK = kSmemQ + kTile;         // 3 boxes
 constexpr int kSmemV = kSmemK + 3 * kTile;     // 3 boxes
 constexpr int kSmemP = kSmemV + 3 * kTile;     // 6 boxes: P[128][384] as 6 K-blocks of 64 keys
 constexpr int kSmemBar = kSmemP + 6 * kTile;
-constexpr int kSmemBytes = kSmemBar + 256 + 1024;
-constexpr int kThreads = 192;
-constexpr uint32_t kColS = 0, kColO = kWin;    // TMEM columns
+constexpr int kSmemX = kSmemBar + 256;         // (reference, sum) exchange between the two column halves
+constexpr int kSmemBytes = kSmemX + 2 * 2 * 128 * 8 + 1024;
+constexpr int kSoftmaxThreads = 256;          // 8 warps: two per TMEM lane quadrant, 192 columns each
+constexpr int kThreads = 64 + kSoftmaxThreads;
+constexpr uint32_t kColS = 0, kColO = kWin;    // TMEM columns: S 0-383, O0 384-447, O1 448-511
 
 struct Params {
   CUtensorMap tma_qkv;  // 3-D: [3D cols, T, B], box [64, 128, 1]
@@ -82,6 +88,26 @@ __device__ __forceinline__ constexpr uint32_t idesc(int n, bool b_mn_major) {
          (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
 }
 
+struct TileInfo {
+  int b, h, q0, kw0;
+};
+
+__device__ __forceinline__ TileInfo decode_tile(const Params& p, int tile) {
+  TileInfo t;
+  const int qt = tile % p.q_tiles;
+  const int bh = tile / p.q_tiles;
+  t.h = bh % p.H;
+  t.b = bh / p.H;
+  t.q0 = qt * kQ;
+  t.kw0 = t.q0 - kQ;
+  return t;
+}
+
+// The running softmax reference may lag the true row maximum by up to 2^kJump before the row's
+// already-written probabilities are rescaled (by an exact power of two): P then stays <= 2^kJump,
+// far inside bf16/fp32 range, and the final O / sum is independent of the reference.
+constexpr float kJump = 24.0f;
+
 __global__ void __launch_bounds__(kThreads, 1) attn_window_kernel(const __grid_constant__ Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -91,10 +117,11 @@ __global__ void __launch_bounds__(kThreads, 1) attn_window_kernel(const __grid_c
   uint64_t* v_full = bars + 1;    // TMA: 3 V landed
   uint64_t* s_done = bars + 2;    // MMA: S complete (Q/K smem reusable)
   uint64_t* o_done = bars + 3;    // MMA: O complete (V/P smem reusable)
-  uint64_t* s_free = bars + 4;    // softmax: S fully read (128 arrivals)
-  uint64_t* p_full = bars + 5;    // softmax: P written (128 arrivals)
-  uint64_t* o_free = bars + 6;    // epilogue: O fully read (128 arrivals)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* o_free = bars + 4;    // epilogue: O fully read (256 arrivals)
+  uint64_t* s_free = bars + 5;    // [3] 128-column slab j of S fully read
+  uint64_t* p_full = bars + 8;    // [6] 64-key block kb of P written (128 arrivals: the owning half)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  float2* xchg = reinterpret_cast<float2*>(smem + kSmemX);  // [2 parities][2 halves][128 rows] (ref, sum)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -105,9 +132,11 @@ __global__ void __launch_bounds__(kThreads, 1) attn_window_kernel(const __grid_c
     mbar_init(v_full, 1);
     mbar_init(s_done, 1);
     mbar_init(o_done, 1);
-    mbar_init(s_free, 128);
-    mbar_init(p_full, 128);
-    mbar_init(o_free, 128);
+    mbar_init(o_free, kSoftmaxThreads);
+    mbar_init(&s_free[0], 128);  // columns   0-127: half 0 only
+    mbar_init(&s_free[1], 256);  // columns 128-255: both halves
+    mbar_init(&s_free[2], 128);  // columns 256-383: half 1 only
+    for (int kb = 0; kb < 6; ++kb) mbar_init(&p_full[kb], 128);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -118,32 +147,35 @@ __global__ void __launch_bounds__(kThreads, 1) attn_window_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int n_my = (p.total_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                   static_cast<int>(gridDim.x);
 
   if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-        const int qt = tile % p.q_tiles;
-        const int bh = tile / p.q_tiles;
-        const int h = bh % p.H;
-        const int b = bh / p.H;
-        const int q0 = qt * kQ;
-        const int kw0 = q0 - kQ;
-        const uint32_t par = (it & 1) ^ 1;  // wait for the previous tile's completion
-        mbar_wait(s_done, par);
+      for (int i = 0; i < n_my; ++i) {
+        const TileInfo t = decode_tile(p, blockIdx.x + i * gridDim.x);
+        const uint32_t prev = (i & 1) ^ 1;  // parity of tile i-1's completion (passes at i == 0)
+        mbar_wait(s_done, prev);            // S(i-1) done: Q/K smem free
         mbar_expect_tx(qk_full, 4 * kTile);
-        tma_load_3d(smem + kSmemQ, &p.tma_qkv, qk_full, h * kHD, q0, b);
+        tma_load_3d(smem + kSmemQ, &p.tma_qkv, qk_full, t.h * kHD, t.q0, t.b);
 #pragma unroll
         for (int j = 0; j < 3; ++j)
-          tma_load_3d(smem + kSmemK + j * kTile, &p.tma_qkv, qk_full, p.D + h * kHD, kw0 + j * kQ, b);
-        mbar_wait(o_done, par);
+          tma_load_3d(smem + kSmemK + j * kTile, &p.tma_qkv, qk_full, p.D + t.h * kHD,
+                      t.kw0 + j * kQ, t.b);
+        mbar_wait(o_done, prev);            // PV(i-1) done: V smem free
         mbar_expect_tx(v_full, 3 * kTile);
 #pragma unroll
         for (int j = 0; j < 3; ++j)
-          tma_load_3d(smem + kSmemV + j * kTile, &p.tma_qkv, v_full, 2 * p.D + h * kHD, kw0 + j * kQ, b);
+          tma_load_3d(smem + kSmemV + j * kTile, &p.tma_qkv, v_full, 2 * p.D + t.h * kHD,
+                      t.kw0 + j * kQ, t.b);
       }
     }
   } else if (warp == 1) {
+    // -------------------------------------------------------------------- MMA issuer
+    // Per tile i the tensor pipe is fed in the order the softmax warps produce/release things:
+    // PV blocks as soon as each 64-key block of P is written (half 0 -> O0, half 1 -> O1), and the
+    // next tile's Q K^T slab by slab as soon as each 128-column slab of S has been read.
     if (lane == 0) {
       constexpr uint32_t idesc_s = idesc(128, false);
       constexpr uint32_t idesc_o = idesc(kHD, true);
@@ -151,106 +183,80 @@ __global__ void __launch_bounds__(kThreads, 1) attn_window_kernel(const __grid_c
       const uint32_t sk = smem_u32(smem + kSmemK);
       const uint32_t sv = smem_u32(smem + kSmemV);
       const uint32_t sp = smem_u32(smem + kSmemP);
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-        const uint32_t par = it & 1;
-        // ---- S = Q K^T
-        mbar_wait(qk_full, par);
-        mbar_wait(s_free, par ^ 1);
+      const uint64_t dq = desc_sw128(sq);
+      auto issue_s_slab = [&](int i, int j) {  // S(i)[:, 128j : 128j+128] = Q K_j^T
+        mbar_wait(&s_free[j], (i & 1) ^ 1);
         tc_fence_after();
-        const uint64_t dq = desc_sw128(sq);
+        const uint64_t dk = desc_sw128(sk + j * kTile);
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          const uint64_t dk = desc_sw128(sk + j * kTile);
+        for (int k = 0; k < kHD / 16; ++k)
+          umma_bf16(tmem_base + kColS + j * 128, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+      };
+      auto issue_pv_block = [&](int i, int kb) {  // O_{kb/3} += P[:, 64kb : 64kb+64] V[64kb : 64kb+64]
+        mbar_wait(&p_full[kb], i & 1);
+        tc_fence_after();
+        const uint64_t dp = desc_sw128(sp + kb * kTile);
+        const uint64_t dv = desc_sw128(sv + (kb >> 1) * kTile + (kb & 1) * (64 * 128));
+        const uint32_t d_o = tmem_base + kColO + (kb >= 3 ? kHD : 0);
 #pragma unroll
-          for (int k = 0; k < kHD / 16; ++k)
-            umma_bf16(tmem_base + kColS + j * 128, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
-        }
+        for (int k = 0; k < 4; ++k)  // 16 keys: +32 B along P's row, +16 rows (2048 B) in V
+          umma_bf16(d_o, dp + 2 * k, dv + 128 * k, idesc_o, ((kb % 3) | k) != 0);
+      };
+      if (n_my > 0) {
+        mbar_wait(qk_full, 0);
+        for (int j = 0; j < 3; ++j) issue_s_slab(0, j);
         umma_commit(s_done);
-        // ---- O = P V
-        mbar_wait(p_full, par);
-        mbar_wait(v_full, par);
-        mbar_wait(o_free, par ^ 1);
-        tc_fence_after();
-#pragma unroll
-        for (int kb = 0; kb < 6; ++kb) {       // 64-key blocks of P; V box j = kb / 2
-          const uint64_t dp = desc_sw128(sp + kb * kTile);
-          const uint64_t dv = desc_sw128(sv + (kb >> 1) * kTile + (kb & 1) * (64 * 128));
-#pragma unroll
-          for (int k = 0; k < 4; ++k)          // 16 keys: +32 B along P's row, +16 rows (2048 B) in V
-            umma_bf16(tmem_base + kColO, dp + 2 * k, dv + 128 * k, idesc_o, (kb | k) != 0);
+      }
+      for (int i = 0; i < n_my; ++i) {
+        const bool has_next = i + 1 < n_my;
+        mbar_wait(v_full, i & 1);
+        mbar_wait(o_free, (i & 1) ^ 1);
+        issue_pv_block(i, 0);
+        issue_pv_block(i, 3);
+        issue_pv_block(i, 1);
+        issue_pv_block(i, 4);
+        if (has_next) {
+          mbar_wait(qk_full, (i + 1) & 1);
+          issue_s_slab(i + 1, 0);
         }
+        issue_pv_block(i, 2);
+        issue_pv_block(i, 5);
         umma_commit(o_done);
+        if (has_next) {
+          issue_s_slab(i + 1, 1);
+          issue_s_slab(i + 1, 2);
+          umma_commit(s_done);
+        }
       }
     }
   } else {
+    // ---------------------- softmax + epilogue: two threads per query row, 192 window columns each
+    // S is read from TMEM exactly once; each 32-column chunk is exponentiated against a running
+    // integer reference (log2 domain) private to the thread.  The two halves of a row never
+    // reconcile their references in P: they accumulate into separate O accumulators (O0, O1) and
+    // the epilogue combines them as (2^r0 O0 + 2^r1 O1) / (2^r0 sum0 + 2^r1 sum1).
     const int quad = warp & 3;
-    const int row = quad * 32 + lane;  // query row within the tile == TMEM lane
+    const int half = (warp - 2) >> 2;
+    const int row = quad * 32 + lane;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     uint8_t* p_row = smem + kSmemP + row * 128;
     const int swz = row & 7;
-    uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-      const int qt = tile % p.q_tiles;
-      const int bh = tile / p.q_tiles;
-      const int h = bh % p.H;
-      const int b = bh / p.H;
-      const int q0 = qt * kQ;
-      const int kw0 = q0 - kQ;
-      const uint32_t par = it & 1;
-      // per-row allowed column range [c_lo, c_hi] inside the window
-      int c_lo = max(row + p.lo, -kw0);
-      int c_hi = min(row + p.hi, p.T - 1 - kw0);
-      c_lo = max(c_lo, 0);
-      c_hi = min(c_hi, kWin - 1);
-      // warp-uniform chunk range that contains any allowed column of any row of this warp
-      const int w_lo = max(max(quad * 32 + p.lo, -kw0), 0);
-      const int w_hi = min(min(quad * 32 + 31 + p.hi, p.T - 1 - kw0), kWin - 1);
-      const int ch_lo = w_lo >> 5, ch_hi = w_hi >> 5;
+    const int cbeg = half * 6;  // this thread's chunks: [cbeg, cbeg + 6)
 
-      mbar_wait(s_done, par);
-      tc_fence_after();
-      // ---- pass 1: row max
-      float mx = -INFINITY;
-      for (int c = ch_lo; c <= ch_hi; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(t_lane + kColS + c * 32, r);
-        tmem_ld_wait();
-        const int base = c * 32;
-        if (base >= c_lo && base + 31 <= c_hi) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (base + i >= c_lo && base + i <= c_hi) mx = fmaxf(mx, __uint_as_float(r[i]));
-        }
-      }
-      const float moff = (mx == -INFINITY ? 0.f : mx) * p.scale_log2;
-      // ---- pass 2: p = exp2(s*scale - max*scale), row sum, P -> smem (bf16, A-operand layout)
-      float sum = 0.f;
-      for (int c = 0; c < kWin / 32; ++c) {
-        uint32_t packed[16];
-        if (c < ch_lo || c > ch_hi) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) packed[i] = 0u;
-        } else {
-          uint32_t r[32];
-          tmem_ld_32x32(t_lane + kColS + c * 32, r);
-          tmem_ld_wait();
-          const int base = c * 32;
-          const bool inner = base >= c_lo && base + 31 <= c_hi;
-          float pv[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float e = fast_exp2(fmaf(__uint_as_float(r[i]), p.scale_log2, -moff));
-            if (!inner && (base + i < c_lo || base + i > c_hi)) e = 0.f;
-            pv[i] = e;
-            sum += e;
-          }
-#pragma unroll
-          for (int i = 0; i < 16; ++i) packed[i] = pack_bf16(pv[2 * i], pv[2 * i + 1]);
-        }
+    for (int i = 0; i < n_my; ++i) {
+      const TileInfo t = decode_tile(p, blockIdx.x + i * gridDim.x);
+      const uint32_t par = i & 1;
+      // allowed columns of this row, and the chunk range any row of this warp needs
+      const int c_lo = max(max(row + p.lo, -t.kw0), 0);
+      const int c_hi = min(min(row + p.hi, p.T - 1 - t.kw0), kWin - 1);
+      const int ch_lo = max(max(quad * 32 + p.lo, -t.kw0), 0) >> 5;
+      const int ch_hi = min(min(quad * 32 + 31 + p.hi, p.T - 1 - t.kw0), kWin - 1) >> 5;
+      auto in_range = [&](int c) { return c >= ch_lo && c <= ch_hi; };
+
+      float ref = -INFINITY;  // running reference (integer-valued, log2 domain)
+      float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
+
+      auto store_chunk = [&](int c, const uint32_t(&packed)[16]) {
         // 32 keys = 64 B = four 16-byte chunks of the 128-byte row in K-block c/2
         uint8_t* blk = p_row + (c >> 1) * kTile;
 #pragma unroll
@@ -259,39 +265,139 @@ __global__ void __launch_bounds__(kThreads, 1) attn_window_kernel(const __grid_c
           *reinterpret_cast<uint4*>(blk + ((chunk ^ swz) << 4)) =
               make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
         }
-      }
-      tc_fence_before();
-      mbar_arrive(s_free);
-      fence_proxy_async_smem();
-      mbar_arrive(p_full);
+      };
+      // rare: the reference moved up by more than kJump: rescale what this thread already wrote
+      auto rescale_written = [&](int c_end, float factor) {
+        for (int cc = cbeg; cc < c_end; ++cc) {
+          uint8_t* blk = p_row + (cc >> 1) * kTile;
+          for (int j = 0; j < 4; ++j) {
+            const int chunk = (cc & 1) * 4 + j;
+            uint4* ptr = reinterpret_cast<uint4*>(blk + ((chunk ^ swz) << 4));
+            uint4 w = *ptr;
+            uint32_t* e = reinterpret_cast<uint32_t*>(&w);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 f = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&e[k]));
+              e[k] = pack_bf16(f.x * factor, f.y * factor);
+            }
+            *ptr = w;
+          }
+        }
+        sum0 *= factor; sum1 *= factor; sum2 *= factor; sum3 *= factor;
+      };
+      auto emit = [&](uint32_t(&v)[32], int c) {
+        uint32_t packed[16];
+        if (!in_range(c)) {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) packed[k] = 0u;
+          store_chunk(c, packed);
+          return;
+        }
+        const int base = c * 32;
+        if (!(base >= c_lo && base + 31 <= c_hi)) {  // boundary chunk: masked scores become -inf
+          const int klo = c_lo - base, khi = c_hi - base;
+#pragma unroll
+          for (int k = 0; k < 32; ++k)
+            if (k < klo || k > khi) v[k] = 0xff800000u;
+        }
+        float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < 32; k += 2) {
+          m0 = fmaxf(m0, __uint_as_float(v[k]));
+          m1 = fmaxf(m1, __uint_as_float(v[k + 1]));
+        }
+        const float cm = fmaxf(m0, m1) * p.scale_log2;
+        if (cm > ref + kJump) {  // also taken on the thread's first allowed chunk (ref = -inf)
+          const float new_ref = ceilf(cm);
+          // a block of P already handed to the tensor pipe is never rescaled: blocks are only
+          // published (p_full) pairwise below, and a published block's reference is final for
+          // the MMA because the correction is applied to everything this thread wrote so far
+          // BEFORE the next publication -- see the note at the publication site.
+          if (ref != -INFINITY) rescale_written(c, fast_exp2(ref - new_ref));
+          ref = new_ref;
+        }
+        const float off = (ref == -INFINITY) ? 0.f : ref;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {  // two groups of 16 columns keep the live register set small
+          float pv[16];
+#pragma unroll
+          for (int k = 0; k < 16; ++k)
+            pv[k] = fast_exp2(fmaf(__uint_as_float(v[16 * g + k]), p.scale_log2, -off));
+#pragma unroll
+          for (int k = 0; k < 16; k += 4) {
+            sum0 += pv[k];
+            sum1 += pv[k + 1];
+            sum2 += pv[k + 2];
+            sum3 += pv[k + 3];
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) packed[8 * g + k] = pack_bf16(pv[2 * k], pv[2 * k + 1]);
+        }
+        store_chunk(c, packed);
+      };
 
-      // ---- epilogue: O / sum -> bf16 -> global
+      mbar_wait(s_done, par);
+      tc_fence_after();
+
+      uint32_t ra[32], rb[32];
+      if (in_range(cbeg)) tmem_ld_32x32(t_lane + kColS + cbeg * 32, ra);
+#pragma unroll 1  // keep the body (2 x emit) resident in the instruction cache
+      for (int u = 0; u < 6; u += 2) {
+        const int c = cbeg + u;
+        tmem_ld_wait();
+        if (in_range(c + 1)) tmem_ld_32x32(t_lane + kColS + (c + 1) * 32, rb);
+        emit(ra, c);
+        tmem_ld_wait();
+        if (u + 2 < 6 && in_range(c + 2)) tmem_ld_32x32(t_lane + kColS + (c + 2) * 32, ra);
+        emit(rb, c + 1);
+        // release slabs of S: half 0 owns chunks 0-5 (slab 0, first half of slab 1), half 1 6-11
+        if ((half == 0 && u == 2) || (half == 1 && u == 0) || u == 4) {
+          const int slab = (half == 0) ? (u == 2 ? 0 : 1) : (u == 0 ? 1 : 2);
+          tc_fence_before();
+          mbar_arrive(&s_free[slab]);
+        }
+        if (u == 4) {
+          // Publish this thread's three P blocks together, after its last chunk: an earlier block
+          // could otherwise be consumed by the tensor pipe and then invalidated by a reference jump.
+          fence_proxy_async_smem();
+          mbar_arrive(&p_full[half * 3 + 0]);
+          mbar_arrive(&p_full[half * 3 + 1]);
+          mbar_arrive(&p_full[half * 3 + 2]);
+        }
+      }
+      const float sum = (sum0 + sum1) + (sum2 + sum3);
+      float2* xc = xchg + par * 256;
+      xc[half * 128 + row] = make_float2(ref, sum);
+      named_bar_sync(1, kSoftmaxThreads);
+      const float2 other = xc[(half ^ 1) * 128 + row];
+
+      // ---- epilogue: (w0 O0 + w1 O1) / (w0 sum0 + w1 sum1) -> bf16 -> global (32 dims per thread)
       mbar_wait(o_done, par);
       tc_fence_after();
       uint32_t o0[32], o1[32];
-      tmem_ld_32x32(t_lane + kColO, o0);
-      tmem_ld_32x32(t_lane + kColO + 32, o1);
+      tmem_ld_32x32(t_lane + kColO + half * 32, o0);
+      tmem_ld_32x32(t_lane + kColO + kHD + half * 32, o1);
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(o_free);
-      const int q = q0 + row;
+      const int q = t.q0 + row;
       if (q < p.T) {
-        const float inv = 1.0f / sum;
-        uint4* dst = reinterpret_cast<uint4*>(p.out + (static_cast<int64_t>(b) * p.T + q) * p.D + h * kHD);
+        const float r_a = half == 0 ? ref : other.x, r_b = half == 0 ? other.x : ref;
+        const float s_a = half == 0 ? sum : other.y, s_b = half == 0 ? other.y : sum;
+        const float rmax = fmaxf(r_a, r_b);
+        const float w_a = (r_a == -INFINITY) ? 0.f : fast_exp2(r_a - rmax);
+        const float w_b = (r_b == -INFINITY) ? 0.f : fast_exp2(r_b - rmax);
+        const float inv = 1.0f / (w_a * s_a + w_b * s_b);
+        const float ka = w_a * inv, kb2 = w_b * inv;
+        uint4* dst = reinterpret_cast<uint4*>(p.out + (static_cast<int64_t>(t.b) * p.T + q) * p.D +
+                                              t.h * kHD + half * 32);
+        auto mix = [&](int k) {
+          return fmaf(__uint_as_float(o0[k]), ka, __uint_as_float(o1[k]) * kb2);
+        };
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          dst[j] = make_uint4(
-              pack_bf16(__uint_as_float(o0[8 * j + 0]) * inv, __uint_as_float(o0[8 * j + 1]) * inv),
-              pack_bf16(__uint_as_float(o0[8 * j + 2]) * inv, __uint_as_float(o0[8 * j + 3]) * inv),
-              pack_bf16(__uint_as_float(o0[8 * j + 4]) * inv, __uint_as_float(o0[8 * j + 5]) * inv),
-              pack_bf16(__uint_as_float(o0[8 * j + 6]) * inv, __uint_as_float(o0[8 * j + 7]) * inv));
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          dst[4 + j] = make_uint4(
-              pack_bf16(__uint_as_float(o1[8 * j + 0]) * inv, __uint_as_float(o1[8 * j + 1]) * inv),
-              pack_bf16(__uint_as_float(o1[8 * j + 2]) * inv, __uint_as_float(o1[8 * j + 3]) * inv),
-              pack_bf16(__uint_as_float(o1[8 * j + 4]) * inv, __uint_as_float(o1[8 * j + 5]) * inv),
-              pack_bf16(__uint_as_float(o1[8 * j + 6]) * inv, __uint_as_float(o1[8 * j + 7]) * inv));
+          dst[j] = make_uint4(pack_bf16(mix(8 * j + 0), mix(8 * j + 1)), pack_bf16(mix(8 * j + 2), mix(8 * j + 3)),
+                              pack_bf16(mix(8 * j + 4), mix(8 * j + 5)), pack_bf16(mix(8 * j + 6), mix(8 * j + 7)));
       }
     }
   }

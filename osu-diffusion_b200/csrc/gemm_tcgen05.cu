@@ -33,7 +33,6 @@ constexpr int UMMA_K = 16;
 constexpr int kMaxSeg = 3;
 constexpr int kStageBytesA = BM * BK * 2;
 constexpr int kStagingBytes = BM * 128;  // one epilogue chunk: 128 rows x 128 B
-constexpr int kNumThreads = 192;
 
 struct GemmParams {
   CUtensorMap tma_a[kMaxSeg];
@@ -77,21 +76,26 @@ __device__ __forceinline__ constexpr uint32_t umma_idesc() {
 }
 
 __device__ __forceinline__ float gelu_tanh(float x) {
-  // 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3))), tanh(u) = 1 - 2 / (1 + e^{2u})
-  const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
-  const float e = __expf(2.0f * u);
-  const float t = 1.0f - __fdividef(2.0f, 1.0f + e);
-  return 0.5f * x * (1.0f + t);
+  // 0.5 x (1 + tanh(u)) = x * sigmoid(2u) = x / (1 + 2^(-2 u log2 e)),
+  // u = sqrt(2/pi) (x + 0.044715 x^3): 4 FMA-pipe ops + ex2 + rcp per element.
+  constexpr float k1 = -2.0f * 0.7978845608028654f * 1.4426950408889634f;
+  constexpr float k3 = k1 * 0.044715f;
+  const float w = fmaf(x * x, k3, k1);
+  const float e = fast_exp2(x * w);
+  return __fdividef(x, 1.0f + e);
 }
 
 enum : int { EPI_F32 = 0, EPI_BF16 = 1, EPI_BF16_GELU = 2 };
 
+__host__ __device__ constexpr int epi_threads(int epi) { return epi == EPI_F32 ? 128 : 256; }
+
 template <int BN, int EPI>
-__global__ void __launch_bounds__(kNumThreads, 1)
+__global__ void __launch_bounds__(64 + epi_threads(EPI), 1)
 gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
   using C = Cfg<BN>;
   constexpr int kEpiCols = (EPI == EPI_F32) ? 32 : 64;  // 128 bytes of output per row per chunk
   constexpr int kChunks = BN / kEpiCols;
+  constexpr int kEpiThreads = epi_threads(EPI);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -121,7 +125,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 128);
+      mbar_init(&tmem_empty[i], kEpiThreads);
     }
     fence_mbar_init();
   }
@@ -187,8 +191,12 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
     }
   } else {
     // ---------------------------------------------------------------- epilogue
+    // fp32 output: 4 warps, one per TMEM lane quadrant, 32 columns (128 B) per chunk.
+    // bf16 output: 8 warps, two per quadrant; each takes 32 of the chunk's 64 columns, which keeps
+    // two warps per scheduler in flight to hide the TMEM-load / MUFU (GELU) latencies.
     const int ep_tid = threadIdx.x - 64;
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may read
+    const int quad = warp & 3;           // TMEM lane quadrant this warp may read
+    const int half = (warp - 2) >> 2;    // which 32-column half of a bf16 chunk (0 for fp32)
     const int row = quad * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -205,55 +213,52 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
         uint8_t* buf = staging + (chunk_ctr & 1) * kStagingBytes;
         // the store that last read this buffer (2 chunks ago) must have drained it
         if (ep_tid == 0) tma_store_wait_read<1>();
-        named_bar_sync(1, 128);
+        named_bar_sync(1, kEpiThreads);
         const int ncol0 = n0 + c * kEpiCols;
         uint8_t* my_row = buf + row * 128;
+        uint32_t r[32];
+        tmem_ld_32x32(t_row + static_cast<uint32_t>(c * kEpiCols + half * 32), r);
+        tmem_ld_wait();
+        if (c == kChunks - 1) {
+          // accumulator fully read: hand the TMEM stage back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(&tmem_empty[acc]);
+        }
+        float v[32];
 #pragma unroll
-        for (int h = 0; h < kEpiCols / 32; ++h) {
-          uint32_t r[32];
-          tmem_ld_32x32(t_row + static_cast<uint32_t>(c * kEpiCols + h * 32), r);
-          tmem_ld_wait();
-          if (c == kChunks - 1 && h == kEpiCols / 32 - 1) {
-            // accumulator fully read: hand the TMEM stage back to the MMA warp
-            tc_fence_before();
-            mbar_arrive(&tmem_empty[acc]);
+        for (int i = 0; i < 32; i += 4) {
+          const int n = ncol0 + half * 32 + i;
+          float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias != nullptr && n + 3 < p.N) b = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+          v[i + 0] = __uint_as_float(r[i + 0]) + b.x;
+          v[i + 1] = __uint_as_float(r[i + 1]) + b.y;
+          v[i + 2] = __uint_as_float(r[i + 2]) + b.z;
+          v[i + 3] = __uint_as_float(r[i + 3]) + b.w;
+        }
+        if (EPI == EPI_BF16_GELU) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = gelu_tanh(v[i]);
+        }
+        if (EPI == EPI_F32) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {  // 8 x 16 B
+            float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            *reinterpret_cast<float4*>(my_row + ((j ^ (row & 7)) << 4)) = o;
           }
-          float v[32];
+        } else {
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const int n = ncol0 + h * 32 + i;
-            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.bias != nullptr && n + 3 < p.N) b = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-            v[i + 0] = __uint_as_float(r[i + 0]) + b.x;
-            v[i + 1] = __uint_as_float(r[i + 1]) + b.y;
-            v[i + 2] = __uint_as_float(r[i + 2]) + b.z;
-            v[i + 3] = __uint_as_float(r[i + 3]) + b.w;
-          }
-          if (EPI == EPI_BF16_GELU) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = gelu_tanh(v[i]);
-          }
-          if (EPI == EPI_F32) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {  // 8 x 16 B
-              float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-              *reinterpret_cast<float4*>(my_row + ((j ^ (row & 7)) << 4)) = o;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {  // 4 x 16 B (8 bf16 each) per 32 columns
-              uint4 o;
-              o.x = pack_bf16(v[8 * j + 0], v[8 * j + 1]);
-              o.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
-              o.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
-              o.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
-              const int jj = h * 4 + j;
-              *reinterpret_cast<uint4*>(my_row + ((jj ^ (row & 7)) << 4)) = o;
-            }
+          for (int j = 0; j < 4; ++j) {  // 4 x 16 B (8 bf16 each) per 32 columns
+            uint4 o;
+            o.x = pack_bf16(v[8 * j + 0], v[8 * j + 1]);
+            o.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+            o.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
+            o.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+            const int jj = half * 4 + j;
+            *reinterpret_cast<uint4*>(my_row + ((jj ^ (row & 7)) << 4)) = o;
           }
         }
         fence_proxy_async_smem();
-        named_bar_sync(1, 128);
+        named_bar_sync(1, kEpiThreads);
         if (ep_tid == 0) {
           tma_store_2d(&p.tma_out, buf, ncol0, m0);
           tma_store_commit();
@@ -372,7 +377,7 @@ static int launch(const GemmParams& p, cudaStream_t stream) {
   }
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, kNumThreads, C::kSmemBytes, stream>>>(p);
+  kern<<<grid, 64 + epi_threads(EPI), C::kSmemBytes, stream>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(-6, cudaGetErrorString(e));
   return 0;

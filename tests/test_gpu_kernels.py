@@ -203,7 +203,7 @@ def test_timestep_features_and_silu_split():
     l2 = torch.empty_like(h2)
     ops.silu_split(a, h2, l2, a_index=idx, table=table, y=yy)
     ref2 = torch.nn.functional.silu(a[idx.long()] + table[yy])
-    assert float((h2.float() + l2.float() - ref2).abs().max()) < 5e-5
+    assert float(((h2.float() + l2.float() - ref2).abs() / ref2.abs().clamp_min(1.0)).max()) < 2e-5
 
 
 # ---------------------------------------------------------------------- diffusion step
