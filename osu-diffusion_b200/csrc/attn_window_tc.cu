@@ -47,7 +47,7 @@ constexpr int kSmemV = kSmemK + 3 * kTile;     // 3 boxes
 constexpr int kSmemP = kSmemV + 3 * kTile;     // 6 boxes: P[128][384] as 6 K-blocks of 64 keys
 constexpr int kSmemBar = kSmemP + 6 * kTile;
 constexpr int kSmemX = kSmemBar + 256;         // (reference, sum) exchange between the two column halves
-constexpr int kSmemBytes = kSmemX + 2 * 2 * 128 * 8 + 1024;
+constexpr int kSmemBytes = kSmemX + 2 * 128 * 8 + 1024;
 constexpr int kSoftmaxThreads = 256;          // 8 warps: two per TMEM lane quadrant, 192 columns each
 constexpr int kThreads = 64 + kSoftmaxThreads;
 constexpr uint32_t kColS = 0, kColO = kWin;    // TMEM columns: S 0-383, O0 384-447, O1 448-511
@@ -115,13 +115,14 @@ __global__ void __launch_bounds__(kThreads, 1) attn_window_kernel(const __grid_c
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemBar);
   uint64_t* qk_full = bars + 0;   // TMA: Q + 3 K landed
   uint64_t* v_full = bars + 1;    // TMA: 3 V landed
-  uint64_t* s_done = bars + 2;    // MMA: S complete (Q/K smem reusable)
-  uint64_t* o_done = bars + 3;    // MMA: O complete (V/P smem reusable)
-  uint64_t* o_free = bars + 4;    // epilogue: O fully read (256 arrivals)
-  uint64_t* s_free = bars + 5;    // [3] 128-column slab j of S fully read
-  uint64_t* p_full = bars + 8;    // [6] 64-key block kb of P written (128 arrivals: the owning half)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
-  float2* xchg = reinterpret_cast<float2*>(smem + kSmemX);  // [2 parities][2 halves][128 rows] (ref, sum)
+  uint64_t* s01_done = bars + 2;  // MMA: slabs 0,1 of S complete (what half 0 reads)
+  uint64_t* s_done = bars + 3;    // MMA: all of S complete (half 1 may start; Q/K smem reusable)
+  uint64_t* o_done = bars + 4;    // [2] MMA: O_h complete (P_h smem reusable; after [1]: V reusable)
+  uint64_t* o_free = bars + 6;    // epilogue: O0 and O1 fully read (128 arrivals, half 1)
+  uint64_t* s_free = bars + 7;    // [3] 128-column slab j of S fully read
+  uint64_t* p_full = bars + 10;   // [2] P_h written (128 arrivals: the owning half)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  float2* xchg = reinterpret_cast<float2*>(smem + kSmemX);  // [2 parities][128 rows] half 0's (ref, sum)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -130,13 +131,16 @@ __global__ void __launch_bounds__(kThreads, 1) attn_window_kernel(const __grid_c
     tma_prefetch_desc(&p.tma_qkv);
     mbar_init(qk_full, 1);
     mbar_init(v_full, 1);
+    mbar_init(s01_done, 1);
     mbar_init(s_done, 1);
-    mbar_init(o_done, 1);
-    mbar_init(o_free, kSoftmaxThreads);
+    mbar_init(&o_done[0], 1);
+    mbar_init(&o_done[1], 1);
+    mbar_init(o_free, 128);
     mbar_init(&s_free[0], 128);  // columns   0-127: half 0 only
     mbar_init(&s_free[1], 256);  // columns 128-255: both halves
     mbar_init(&s_free[2], 128);  // columns 256-383: half 1 only
-    for (int kb = 0; kb < 6; ++kb) mbar_init(&p_full[kb], 128);
+    mbar_init(&p_full[0], 128);
+    mbar_init(&p_full[1], 128);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -163,7 +167,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_window_kernel(const __grid_c
         for (int j = 0; j < 3; ++j)
           tma_load_3d(smem + kSmemK + j * kTile, &p.tma_qkv, qk_full, p.D + t.h * kHD,
                       t.kw0 + j * kQ, t.b);
-        mbar_wait(o_done, prev);            // PV(i-1) done: V smem free
+        mbar_wait(&o_done[1], prev);        // PV_1(i-1), the last reader of V(i-1), is done
         mbar_expect_tx(v_full, 3 * kTile);
 #pragma unroll
         for (int j = 0; j < 3; ++j)
@@ -173,9 +177,10 @@ __global__ void __launch_bounds__(kThreads, 1) attn_window_kernel(const __grid_c
     }
   } else if (warp == 1) {
     // -------------------------------------------------------------------- MMA issuer
-    // Per tile i the tensor pipe is fed in the order the softmax warps produce/release things:
-    // PV blocks as soon as each 64-key block of P is written (half 0 -> O0, half 1 -> O1), and the
-    // next tile's Q K^T slab by slab as soon as each 128-column slab of S has been read.
+    // The two column halves of the softmax run staggered (half 0 starts as soon as slabs 0,1 of S
+    // exist, half 1 after slab 2), so the tensor pipe interleaves, per tile i:
+    //   S(i+1) slab 0 | PV_0(i) | S(i+1) slab 1 | S(i+1) slab 2 | PV_1(i)
+    // and each half's MMA latency is hidden behind the other half's exponentials.
     if (lane == 0) {
       constexpr uint32_t idesc_s = idesc(128, false);
       constexpr uint32_t idesc_o = idesc(kHD, true);
@@ -192,41 +197,44 @@ __global__ void __launch_bounds__(kThreads, 1) attn_window_kernel(const __grid_c
         for (int k = 0; k < kHD / 16; ++k)
           umma_bf16(tmem_base + kColS + j * 128, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
       };
-      auto issue_pv_block = [&](int i, int kb) {  // O_{kb/3} += P[:, 64kb : 64kb+64] V[64kb : 64kb+64]
-        mbar_wait(&p_full[kb], i & 1);
+      auto issue_pv_half = [&](int i, int h) {  // O_h = P[:, 192h : 192h+192] V[192h : 192h+192]
+        mbar_wait(&p_full[h], i & 1);
         tc_fence_after();
-        const uint64_t dp = desc_sw128(sp + kb * kTile);
-        const uint64_t dv = desc_sw128(sv + (kb >> 1) * kTile + (kb & 1) * (64 * 128));
-        const uint32_t d_o = tmem_base + kColO + (kb >= 3 ? kHD : 0);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)  // 16 keys: +32 B along P's row, +16 rows (2048 B) in V
-          umma_bf16(d_o, dp + 2 * k, dv + 128 * k, idesc_o, ((kb % 3) | k) != 0);
+        for (int b3 = 0; b3 < 3; ++b3) {
+          const int kb = 3 * h + b3;           // 64-key block of P; V box = kb / 2
+          const uint64_t dp = desc_sw128(sp + kb * kTile);
+          const uint64_t dv = desc_sw128(sv + (kb >> 1) * kTile + (kb & 1) * (64 * 128));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)          // 16 keys: +32 B along P's row, +16 rows (2048 B) in V
+            umma_bf16(tmem_base + kColO + h * kHD, dp + 2 * k, dv + 128 * k, idesc_o, (b3 | k) != 0);
+        }
+        umma_commit(&o_done[h]);
       };
       if (n_my > 0) {
         mbar_wait(qk_full, 0);
-        for (int j = 0; j < 3; ++j) issue_s_slab(0, j);
+        issue_s_slab(0, 0);
+        issue_s_slab(0, 1);
+        umma_commit(s01_done);
+        issue_s_slab(0, 2);
         umma_commit(s_done);
       }
       for (int i = 0; i < n_my; ++i) {
         const bool has_next = i + 1 < n_my;
-        mbar_wait(v_full, i & 1);
-        mbar_wait(o_free, (i & 1) ^ 1);
-        issue_pv_block(i, 0);
-        issue_pv_block(i, 3);
-        issue_pv_block(i, 1);
-        issue_pv_block(i, 4);
         if (has_next) {
           mbar_wait(qk_full, (i + 1) & 1);
           issue_s_slab(i + 1, 0);
         }
-        issue_pv_block(i, 2);
-        issue_pv_block(i, 5);
-        umma_commit(o_done);
+        mbar_wait(v_full, i & 1);
+        mbar_wait(o_free, (i & 1) ^ 1);
+        issue_pv_half(i, 0);
         if (has_next) {
           issue_s_slab(i + 1, 1);
+          umma_commit(s01_done);
           issue_s_slab(i + 1, 2);
           umma_commit(s_done);
         }
+        issue_pv_half(i, 1);
       }
     }
   } else {
@@ -234,7 +242,8 @@ __global__ void __launch_bounds__(kThreads, 1) attn_window_kernel(const __grid_c
     // S is read from TMEM exactly once; each 32-column chunk is exponentiated against a running
     // integer reference (log2 domain) private to the thread.  The two halves of a row never
     // reconcile their references in P: they accumulate into separate O accumulators (O0, O1) and
-    // the epilogue combines them as (2^r0 O0 + 2^r1 O1) / (2^r0 sum0 + 2^r1 sum1).
+    // the epilogue (done by half 1, which finishes last) combines them as
+    // (2^r0 O0 + 2^r1 O1) / (2^r0 sum0 + 2^r1 sum1).
     const int quad = warp & 3;
     const int half = (warp - 2) >> 2;
     const int row = quad * 32 + lane;
@@ -267,6 +276,8 @@ __global__ void __launch_bounds__(kThreads, 1) attn_window_kernel(const __grid_c
         }
       };
       // rare: the reference moved up by more than kJump: rescale what this thread already wrote
+      // (nothing of it has been published to the tensor pipe yet: p_full[half] fires after the
+      // thread's last chunk)
       auto rescale_written = [&](int c_end, float factor) {
         for (int cc = cbeg; cc < c_end; ++cc) {
           uint8_t* blk = p_row + (cc >> 1) * kTile;
@@ -309,10 +320,6 @@ __global__ void __launch_bounds__(kThreads, 1) attn_window_kernel(const __grid_c
         const float cm = fmaxf(m0, m1) * p.scale_log2;
         if (cm > ref + kJump) {  // also taken on the thread's first allowed chunk (ref = -inf)
           const float new_ref = ceilf(cm);
-          // a block of P already handed to the tensor pipe is never rescaled: blocks are only
-          // published (p_full) pairwise below, and a published block's reference is final for
-          // the MMA because the correction is applied to everything this thread wrote so far
-          // BEFORE the next publication -- see the note at the publication site.
           if (ref != -INFINITY) rescale_written(c, fast_exp2(ref - new_ref));
           ref = new_ref;
         }
@@ -336,7 +343,9 @@ __global__ void __launch_bounds__(kThreads, 1) attn_window_kernel(const __grid_c
         store_chunk(c, packed);
       };
 
-      mbar_wait(s_done, par);
+      // S slabs this half reads exist; PV_half(i-1) has finished reading this half's P blocks
+      mbar_wait(half == 0 ? s01_done : s_done, par);
+      if (i > 0) mbar_wait(&o_done[half], par ^ 1);
       tc_fence_after();
 
       uint32_t ra[32], rb[32];
@@ -356,48 +365,54 @@ __global__ void __launch_bounds__(kThreads, 1) attn_window_kernel(const __grid_c
           tc_fence_before();
           mbar_arrive(&s_free[slab]);
         }
-        if (u == 4) {
-          // Publish this thread's three P blocks together, after its last chunk: an earlier block
-          // could otherwise be consumed by the tensor pipe and then invalidated by a reference jump.
-          fence_proxy_async_smem();
-          mbar_arrive(&p_full[half * 3 + 0]);
-          mbar_arrive(&p_full[half * 3 + 1]);
-          mbar_arrive(&p_full[half * 3 + 2]);
-        }
       }
       const float sum = (sum0 + sum1) + (sum2 + sum3);
-      float2* xc = xchg + par * 256;
-      xc[half * 128 + row] = make_float2(ref, sum);
-      named_bar_sync(1, kSoftmaxThreads);
-      const float2 other = xc[(half ^ 1) * 128 + row];
+      float2* xc = xchg + par * 128;
+      if (half == 0) {
+        xc[row] = make_float2(ref, sum);
+        fence_proxy_async_smem();
+        mbar_arrive(&p_full[0]);
+        // publishes xc to half 1 (which bar.syncs); ids alternate per tile because half 0 may
+        // already be one tile ahead of half 1 (never two: s_free[1] ties them together)
+        asm volatile("bar.arrive %0, 256;" ::"r"(1 + static_cast<int>(par)) : "memory");
+        continue;
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(&p_full[1]);
+      named_bar_sync(1 + par, kSoftmaxThreads);
+      const float2 other = xc[row];
 
-      // ---- epilogue: (w0 O0 + w1 O1) / (w0 sum0 + w1 sum1) -> bf16 -> global (32 dims per thread)
-      mbar_wait(o_done, par);
+      // ---- epilogue (half 1): (w0 O0 + w1 O1) / (w0 sum0 + w1 sum1) -> bf16 -> global
+      mbar_wait(&o_done[0], par);
+      mbar_wait(&o_done[1], par);
       tc_fence_after();
-      uint32_t o0[32], o1[32];
-      tmem_ld_32x32(t_lane + kColO + half * 32, o0);
-      tmem_ld_32x32(t_lane + kColO + kHD + half * 32, o1);
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(o_free);
+      const float rmax = fmaxf(other.x, ref);
+      const float w_a = (other.x == -INFINITY) ? 0.f : fast_exp2(other.x - rmax);
+      const float w_b = (ref == -INFINITY) ? 0.f : fast_exp2(ref - rmax);
+      const float inv = 1.0f / (w_a * other.y + w_b * sum);
+      const float ka = w_a * inv, kb2 = w_b * inv;
       const int q = t.q0 + row;
-      if (q < p.T) {
-        const float r_a = half == 0 ? ref : other.x, r_b = half == 0 ? other.x : ref;
-        const float s_a = half == 0 ? sum : other.y, s_b = half == 0 ? other.y : sum;
-        const float rmax = fmaxf(r_a, r_b);
-        const float w_a = (r_a == -INFINITY) ? 0.f : fast_exp2(r_a - rmax);
-        const float w_b = (r_b == -INFINITY) ? 0.f : fast_exp2(r_b - rmax);
-        const float inv = 1.0f / (w_a * s_a + w_b * s_b);
-        const float ka = w_a * inv, kb2 = w_b * inv;
-        uint4* dst = reinterpret_cast<uint4*>(p.out + (static_cast<int64_t>(t.b) * p.T + q) * p.D +
-                                              t.h * kHD + half * 32);
-        auto mix = [&](int k) {
-          return fmaf(__uint_as_float(o0[k]), ka, __uint_as_float(o1[k]) * kb2);
-        };
+      uint4* dst = reinterpret_cast<uint4*>(p.out + (static_cast<int64_t>(t.b) * p.T + q) * p.D + t.h * kHD);
+#pragma unroll 1
+      for (int hh = 0; hh < 2; ++hh) {  // two groups of 32 head dims
+        uint32_t o0[32], o1[32];
+        tmem_ld_32x32(t_lane + kColO + hh * 32, o0);
+        tmem_ld_32x32(t_lane + kColO + kHD + hh * 32, o1);
+        tmem_ld_wait();
+        if (hh == 1) {
+          tc_fence_before();
+          mbar_arrive(o_free);
+        }
+        if (q < p.T) {
+          auto mix = [&](int k) {
+            return fmaf(__uint_as_float(o0[k]), ka, __uint_as_float(o1[k]) * kb2);
+          };
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          dst[j] = make_uint4(pack_bf16(mix(8 * j + 0), mix(8 * j + 1)), pack_bf16(mix(8 * j + 2), mix(8 * j + 3)),
-                              pack_bf16(mix(8 * j + 4), mix(8 * j + 5)), pack_bf16(mix(8 * j + 6), mix(8 * j + 7)));
+          for (int j = 0; j < 4; ++j)
+            dst[hh * 4 + j] =
+                make_uint4(pack_bf16(mix(8 * j + 0), mix(8 * j + 1)), pack_bf16(mix(8 * j + 2), mix(8 * j + 3)),
+                           pack_bf16(mix(8 * j + 4), mix(8 * j + 5)), pack_bf16(mix(8 * j + 6), mix(8 * j + 7)));
+        }
       }
     }
   }
