@@ -115,13 +115,12 @@ __global__ void __launch_bounds__(kThreads, 1) attn_window_kernel(const __grid_c
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemBar);
   uint64_t* qk_full = bars + 0;   // TMA: Q + 3 K landed
   uint64_t* v_full = bars + 1;    // TMA: 3 V landed
-  uint64_t* s01_done = bars + 2;  // MMA: slabs 0,1 of S complete (what half 0 reads)
-  uint64_t* s_done = bars + 3;    // MMA: all of S complete (half 1 may start; Q/K smem reusable)
-  uint64_t* o_done = bars + 4;    // [2] MMA: O_h complete (P_h smem reusable; after [1]: V reusable)
-  uint64_t* o_free = bars + 6;    // epilogue: O0 and O1 fully read (128 arrivals, half 1)
-  uint64_t* s_free = bars + 7;    // [3] 128-column slab j of S fully read
-  uint64_t* p_full = bars + 10;   // [2] P_h written (128 arrivals: the owning half)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* s_done = bars + 2;    // [3] MMA: slab j of S complete ([2] also: Q/K smem reusable)
+  uint64_t* o_done = bars + 5;    // [2] MMA: O_h complete (P_h smem reusable; after [1]: V reusable)
+  uint64_t* o_free = bars + 7;    // epilogue: O0 and O1 fully read (128 arrivals, half 1)
+  uint64_t* s_free = bars + 8;    // [3] 128-column slab j of S fully read
+  uint64_t* p_full = bars + 11;   // [2] P_h written (128 arrivals: the owning half)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
   float2* xchg = reinterpret_cast<float2*>(smem + kSmemX);  // [2 parities][128 rows] half 0's (ref, sum)
 
   const int warp = threadIdx.x >> 5;
@@ -131,8 +130,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_window_kernel(const __grid_c
     tma_prefetch_desc(&p.tma_qkv);
     mbar_init(qk_full, 1);
     mbar_init(v_full, 1);
-    mbar_init(s01_done, 1);
-    mbar_init(s_done, 1);
+    for (int j = 0; j < 3; ++j) mbar_init(&s_done[j], 1);
     mbar_init(&o_done[0], 1);
     mbar_init(&o_done[1], 1);
     mbar_init(o_free, 128);
@@ -160,7 +158,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_window_kernel(const __grid_c
       for (int i = 0; i < n_my; ++i) {
         const TileInfo t = decode_tile(p, blockIdx.x + i * gridDim.x);
         const uint32_t prev = (i & 1) ^ 1;  // parity of tile i-1's completion (passes at i == 0)
-        mbar_wait(s_done, prev);            // S(i-1) done: Q/K smem free
+        mbar_wait(&s_done[2], prev);        // S(i-1) done (slab 2 is issued last): Q/K smem free
         mbar_expect_tx(qk_full, 4 * kTile);
         tma_load_3d(smem + kSmemQ, &p.tma_qkv, qk_full, t.h * kHD, t.q0, t.b);
 #pragma unroll
@@ -177,10 +175,11 @@ __global__ void __launch_bounds__(kThreads, 1) attn_window_kernel(const __grid_c
     }
   } else if (warp == 1) {
     // -------------------------------------------------------------------- MMA issuer
-    // The two column halves of the softmax run staggered (half 0 starts as soon as slabs 0,1 of S
-    // exist, half 1 after slab 2), so the tensor pipe interleaves, per tile i:
-    //   S(i+1) slab 0 | PV_0(i) | S(i+1) slab 1 | S(i+1) slab 2 | PV_1(i)
-    // and each half's MMA latency is hidden behind the other half's exponentials.
+    // Both column halves of the softmax start a tile on slab 1 of S (which both release first) and
+    // finish on their private slab (0 resp. 2), so per tile i the tensor pipe is fed in event order:
+    //   S(i+1) slab 1 | S(i+1) slab 0 | PV_0(i) | S(i+1) slab 2 | PV_1(i)
+    // The halves drift half a period apart, so each half's MMA latency hides behind the other
+    // half's exponentials.
     if (lane == 0) {
       constexpr uint32_t idesc_s = idesc(128, false);
       constexpr uint32_t idesc_o = idesc(kHD, true);
@@ -211,29 +210,27 @@ __global__ void __launch_bounds__(kThreads, 1) attn_window_kernel(const __grid_c
         }
         umma_commit(&o_done[h]);
       };
+      auto issue_s = [&](int i, int j) {
+        issue_s_slab(i, j);
+        umma_commit(&s_done[j]);
+      };
       if (n_my > 0) {
         mbar_wait(qk_full, 0);
-        issue_s_slab(0, 0);
-        issue_s_slab(0, 1);
-        umma_commit(s01_done);
-        issue_s_slab(0, 2);
-        umma_commit(s_done);
+        issue_s(0, 1);
+        issue_s(0, 0);
+        issue_s(0, 2);
       }
       for (int i = 0; i < n_my; ++i) {
         const bool has_next = i + 1 < n_my;
         if (has_next) {
           mbar_wait(qk_full, (i + 1) & 1);
-          issue_s_slab(i + 1, 0);
+          issue_s(i + 1, 1);  // both halves finish their slab-1 chunks first
+          issue_s(i + 1, 0);  // released at the end of half 0
         }
         mbar_wait(v_full, i & 1);
         mbar_wait(o_free, (i & 1) ^ 1);
         issue_pv_half(i, 0);
-        if (has_next) {
-          issue_s_slab(i + 1, 1);
-          umma_commit(s01_done);
-          issue_s_slab(i + 1, 2);
-          umma_commit(s_done);
-        }
+        if (has_next) issue_s(i + 1, 2);  // released at the end of half 1 (slab 2 last: frees Q/K)
         issue_pv_half(i, 1);
       }
     }
@@ -250,7 +247,8 @@ __global__ void __launch_bounds__(kThreads, 1) attn_window_kernel(const __grid_c
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     uint8_t* p_row = smem + kSmemP + row * 128;
     const int swz = row & 7;
-    const int cbeg = half * 6;  // this thread's chunks: [cbeg, cbeg + 6)
+    // this thread's six chunks in processing order: the slab-1 part first, the private slab last
+    auto chunk_of = [&](int u) { return half == 0 ? (u < 2 ? 4 + u : u - 2) : 6 + u; };
 
     for (int i = 0; i < n_my; ++i) {
       const TileInfo t = decode_tile(p, blockIdx.x + i * gridDim.x);
@@ -278,8 +276,9 @@ __global__ void __launch_bounds__(kThreads, 1) attn_window_kernel(const __grid_c
       // rare: the reference moved up by more than kJump: rescale what this thread already wrote
       // (nothing of it has been published to the tensor pipe yet: p_full[half] fires after the
       // thread's last chunk)
-      auto rescale_written = [&](int c_end, float factor) {
-        for (int cc = cbeg; cc < c_end; ++cc) {
+      auto rescale_written = [&](int u_end, float factor) {
+        for (int uu = 0; uu < u_end; ++uu) {
+          const int cc = chunk_of(uu);
           uint8_t* blk = p_row + (cc >> 1) * kTile;
           for (int j = 0; j < 4; ++j) {
             const int chunk = (cc & 1) * 4 + j;
@@ -296,7 +295,8 @@ __global__ void __launch_bounds__(kThreads, 1) attn_window_kernel(const __grid_c
         }
         sum0 *= factor; sum1 *= factor; sum2 *= factor; sum3 *= factor;
       };
-      auto emit = [&](uint32_t(&v)[32], int c) {
+      auto emit = [&](uint32_t(&v)[32], int u) {
+        const int c = chunk_of(u);
         uint32_t packed[16];
         if (!in_range(c)) {
 #pragma unroll
@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_window_kernel(const __grid_c
         const float cm = fmaxf(m0, m1) * p.scale_log2;
         if (cm > ref + kJump) {  // also taken on the thread's first allowed chunk (ref = -inf)
           const float new_ref = ceilf(cm);
-          if (ref != -INFINITY) rescale_written(c, fast_exp2(ref - new_ref));
+          if (ref != -INFINITY) rescale_written(u, fast_exp2(ref - new_ref));
           ref = new_ref;
         }
         const float off = (ref == -INFINITY) ? 0.f : ref;
@@ -343,27 +343,29 @@ __global__ void __launch_bounds__(kThreads, 1) attn_window_kernel(const __grid_c
         store_chunk(c, packed);
       };
 
-      // S slabs this half reads exist; PV_half(i-1) has finished reading this half's P blocks
-      mbar_wait(half == 0 ? s01_done : s_done, par);
+      // slab 1 of S exists; PV_half(i-1) has finished reading this half's P blocks
+      mbar_wait(&s_done[1], par);
       if (i > 0) mbar_wait(&o_done[half], par ^ 1);
       tc_fence_after();
 
       uint32_t ra[32], rb[32];
-      if (in_range(cbeg)) tmem_ld_32x32(t_lane + kColS + cbeg * 32, ra);
+      if (in_range(chunk_of(0))) tmem_ld_32x32(t_lane + kColS + chunk_of(0) * 32, ra);
 #pragma unroll 1  // keep the body (2 x emit) resident in the instruction cache
       for (int u = 0; u < 6; u += 2) {
-        const int c = cbeg + u;
         tmem_ld_wait();
-        if (in_range(c + 1)) tmem_ld_32x32(t_lane + kColS + (c + 1) * 32, rb);
-        emit(ra, c);
+        if (in_range(chunk_of(u + 1))) tmem_ld_32x32(t_lane + kColS + chunk_of(u + 1) * 32, rb);
+        emit(ra, u);
         tmem_ld_wait();
-        if (u + 2 < 6 && in_range(c + 2)) tmem_ld_32x32(t_lane + kColS + (c + 2) * 32, ra);
-        emit(rb, c + 1);
-        // release slabs of S: half 0 owns chunks 0-5 (slab 0, first half of slab 1), half 1 6-11
-        if ((half == 0 && u == 2) || (half == 1 && u == 0) || u == 4) {
-          const int slab = (half == 0) ? (u == 2 ? 0 : 1) : (u == 0 ? 1 : 2);
+        if (u == 0) {  // the remaining four chunks live in this half's private slab
+          mbar_wait(&s_done[half == 0 ? 0 : 2], par);
+          tc_fence_after();
+        }
+        if (u + 2 < 6 && in_range(chunk_of(u + 2)))
+          tmem_ld_32x32(t_lane + kColS + chunk_of(u + 2) * 32, ra);
+        emit(rb, u + 1);
+        if (u == 0 || u == 4) {  // slab 1 after the first pair, the private slab after the last
           tc_fence_before();
-          mbar_arrive(&s_free[slab]);
+          mbar_arrive(&s_free[u == 0 ? 1 : (half == 0 ? 0 : 2)]);
         }
       }
       const float sum = (sum0 + sum1) + (sum2 + sum3);
