@@ -51,6 +51,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Warp-collective forms: one lane polls / arrives for the whole (converged) warp.  With hundreds of
+// threads spinning on try_wait the mbarrier unit saturates and every arrive / complete_tx / commit
+// queues behind the polls, so hand-off latency grows from ~175 cycles to thousands (measured with
+// tools/ubench and the attention kernel's ablations); barrier counts are per WARP accordingly.
+__device__ __forceinline__ void warp_mbar_wait(uint64_t* bar, uint32_t parity) {
+  if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
+  __syncwarp();
+}
+__device__ __forceinline__ void warp_mbar_arrive(uint64_t* bar) {
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
+}
+
 // ----------------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
