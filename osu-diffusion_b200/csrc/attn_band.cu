@@ -24,20 +24,34 @@ namespace osudit {
 constexpr int kBQ = 64;   // queries per CTA
 constexpr int kBKV = 64;  // keys per tile
 
+// Shared-memory tile geometry per head_dim.  hd=64: 128-byte rows, XOR swizzle of the 16-byte chunk
+// index with (row & 7).  hd=72 (DiT-XL, models.py:410-412): rows padded to 80 columns (the extra
+// 16-byte chunk is zero so Q K^T can run 5 k-steps of 16) at a 176-byte pitch, which makes the
+// 8-row ldmatrix fetches bank-conflict free without a swizzle.
 template <int HD>
-__device__ __forceinline__ void load_tile_async(__nv_bfloat16* s, const __nv_bfloat16* g, int64_t ld,
+struct Geo {
+  static constexpr int kChunks = HD / 8;                  // 16-byte chunks of real data per row
+  static constexpr int kKSteps = (HD + 15) / 16;          // k-steps of Q K^T
+  static constexpr int kDBlocks = 2 * ((HD / 8 + 1) / 2); // 8-wide output blocks (even, incl. padding)
+  static constexpr int kPitch = HD == 64 ? 128 : 176;
+  static constexpr int kTileBytes = kBKV * kPitch;
+  static constexpr bool kPadded = (HD % 16) != 0;
+  __device__ static __forceinline__ uint32_t off(int r, int ch) {
+    return HD == 64 ? r * 128 + ((ch ^ (r & 7)) << 4) : r * kPitch + (ch << 4);
+  }
+};
+
+template <int HD>
+__device__ __forceinline__ void load_tile_async(uint8_t* s, const __nv_bfloat16* g, int64_t ld,
                                                 int row0, int T, int tid) {
-  constexpr int kChunks = HD / 8;  // 16-byte chunks per row
-  static_assert(kChunks == 8, "swizzle below assumes 128-byte rows");
-#pragma unroll
-  for (int i = 0; i < (kBKV * kChunks) / 128; ++i) {
-    const int idx = tid + i * 128;
-    const int r = idx >> 3;
-    const int ch = idx & 7;
+  using G = Geo<HD>;
+  for (int idx = tid; idx < kBKV * G::kChunks; idx += 128) {
+    const int r = idx / G::kChunks;
+    const int ch = idx - r * G::kChunks;
     const int row = row0 + r;
     const bool valid = row >= 0 && row < T;
     const __nv_bfloat16* src = g + static_cast<int64_t>(valid ? row : 0) * ld + ch * 8;
-    cp_async_16(reinterpret_cast<uint8_t*>(s) + r * 128 + ((ch ^ (r & 7)) << 4), src, valid);
+    cp_async_16(s + G::off(r, ch), src, valid);
   }
 }
 
@@ -45,9 +59,11 @@ template <int HD>
 __global__ void __launch_bounds__(128)
 attn_band_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int T, int H,
                  int wl, int wr, const uint8_t* __restrict__ mask, float scale_log2) {
-  __shared__ __align__(128) __nv_bfloat16 sQ[kBQ * HD];
-  __shared__ __align__(128) __nv_bfloat16 sK[2][kBKV * HD];
-  __shared__ __align__(128) __nv_bfloat16 sV[2][kBKV * HD];
+  using G = Geo<HD>;
+  extern __shared__ __align__(128) uint8_t smem_attn[];
+  uint8_t* sQ = smem_attn;
+  uint8_t* sK[2] = {sQ + G::kTileBytes, sQ + 2 * G::kTileBytes};
+  uint8_t* sV[2] = {sQ + 3 * G::kTileBytes, sQ + 4 * G::kTileBytes};
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -61,6 +77,12 @@ attn_band_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
   const __nv_bfloat16* gk = gq + D;
   const __nv_bfloat16* gv = gq + 2 * D;
 
+  if (G::kPadded) {  // zero the padding chunk of every row once; cp.async never writes it
+    for (int idx = tid; idx < 5 * kBKV; idx += 128)
+      *reinterpret_cast<uint4*>(smem_attn + (idx / kBKV) * G::kTileBytes + G::off(idx % kBKV, G::kChunks)) =
+          make_uint4(0, 0, 0, 0);
+  }
+
   const int k_first = max(0, q0 - wl);
   const int k_last = min(T - 1, min(q0 + kBQ - 1, T - 1) + wr);
   const int kt_lo = k_first / kBKV;
@@ -71,12 +93,12 @@ attn_band_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
   load_tile_async<HD>(sV[0], gv, ld, kt_lo * kBKV, T, tid);
   cp_async_commit();
 
-  float o_acc[HD / 8][4];
+  float o_acc[G::kDBlocks][4];
 #pragma unroll
-  for (int i = 0; i < HD / 8; ++i) o_acc[i][0] = o_acc[i][1] = o_acc[i][2] = o_acc[i][3] = 0.f;
+  for (int i = 0; i < G::kDBlocks; ++i) o_acc[i][0] = o_acc[i][1] = o_acc[i][2] = o_acc[i][3] = 0.f;
   float m_run[2] = {-INFINITY, -INFINITY};
   float l_run[2] = {0.f, 0.f};
-  uint32_t qf[HD / 16][4];
+  uint32_t qf[G::kKSteps][4];
 
   const int qrow[2] = {q0 + warp * 16 + (lane >> 2), q0 + warp * 16 + (lane >> 2) + 8};
 
@@ -94,10 +116,10 @@ attn_band_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
 
     if (kt == kt_lo) {
 #pragma unroll
-      for (int ks = 0; ks < HD / 16; ++ks) {
+      for (int ks = 0; ks < G::kKSteps; ++ks) {
         const int r = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
         const int ch = ks * 2 + (lane >> 4);
-        ldmatrix_x4(qf[ks], smem_u32(sQ) + r * 128 + ((ch ^ (r & 7)) << 4));
+        ldmatrix_x4(qf[ks], smem_u32(sQ) + G::off(r, ch));
       }
     }
 
@@ -107,13 +129,13 @@ attn_band_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
     for (int nb = 0; nb < kBKV / 8; ++nb) s[nb][0] = s[nb][1] = s[nb][2] = s[nb][3] = 0.f;
     const uint32_t sk = smem_u32(sK[buf]);
 #pragma unroll
-    for (int ks = 0; ks < HD / 16; ++ks) {
+    for (int ks = 0; ks < G::kKSteps; ++ks) {
 #pragma unroll
       for (int nb = 0; nb < kBKV / 8; nb += 2) {
         uint32_t kf[4];
         const int r = nb * 8 + (lane & 7) + ((lane >> 4) & 1) * 8;
         const int ch = ks * 2 + ((lane >> 3) & 1);
-        ldmatrix_x4(kf, sk + r * 128 + ((ch ^ (r & 7)) << 4));
+        ldmatrix_x4(kf, sk + G::off(r, ch));
         mma_bf16_16816(s[nb], qf[ks], kf[0], kf[1]);
         mma_bf16_16816(s[nb + 1], qf[ks], kf[2], kf[3]);
       }
@@ -161,7 +183,7 @@ attn_band_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
       l_run[rr] = l_run[rr] * corr + sum;
       m_run[rr] = m_new;
 #pragma unroll
-      for (int db = 0; db < HD / 8; ++db) {
+      for (int db = 0; db < G::kDBlocks; ++db) {
         o_acc[db][2 * rr] *= corr;
         o_acc[db][2 * rr + 1] *= corr;
       }
@@ -177,11 +199,11 @@ attn_band_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
       pf[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
       pf[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
 #pragma unroll
-      for (int db = 0; db < HD / 8; db += 2) {
+      for (int db = 0; db < G::kDBlocks; db += 2) {
         uint32_t vf[4];
         const int r = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
         const int ch = db + (lane >> 4);
-        ldmatrix_x4_trans(vf, sv + r * 128 + ((ch ^ (r & 7)) << 4));
+        ldmatrix_x4_trans(vf, sv + G::off(r, ch));
         mma_bf16_16816(o_acc[db], pf, vf[0], vf[1]);
         mma_bf16_16816(o_acc[db + 1], pf, vf[2], vf[3]);
       }
@@ -198,25 +220,40 @@ attn_band_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
     const float inv = 1.0f / l;  // 0/0 -> NaN for a fully masked row, as the reference's softmax
     const int r = warp * 16 + (lane >> 2) + rr * 8;
 #pragma unroll
-    for (int db = 0; db < HD / 8; ++db) {
+    for (int db = 0; db < G::kChunks; ++db) {
       const uint32_t v = pack_bf16(o_acc[db][2 * rr] * inv, o_acc[db][2 * rr + 1] * inv);
-      uint8_t* dst = reinterpret_cast<uint8_t*>(sQ) + r * 128 + ((db ^ (r & 7)) << 4) + (lane & 3) * 4;
-      *reinterpret_cast<uint32_t*>(dst) = v;
+      *reinterpret_cast<uint32_t*>(sQ + G::off(r, db) + (lane & 3) * 4) = v;
     }
   }
   __syncthreads();
   __nv_bfloat16* go = out + static_cast<int64_t>(b) * T * D + h * HD;
-#pragma unroll
-  for (int i = 0; i < (kBQ * HD / 8) / 128; ++i) {
-    const int idx = tid + i * 128;
-    const int r = idx >> 3;
-    const int ch = idx & 7;
+  for (int idx = tid; idx < kBQ * G::kChunks; idx += 128) {
+    const int r = idx / G::kChunks;
+    const int ch = idx - r * G::kChunks;
     if (q0 + r < T) {
-      const uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<uint8_t*>(sQ) + r * 128 +
-                                                      ((ch ^ (r & 7)) << 4));
+      const uint4 v = *reinterpret_cast<const uint4*>(sQ + G::off(r, ch));
       *reinterpret_cast<uint4*>(go + static_cast<int64_t>(q0 + r) * D + ch * 8) = v;
     }
   }
+}
+
+template <int HD>
+static int launch_band(const void* qkv, void* out, int B, int T, int H, int wl, int wr,
+                       const uint8_t* mask, cudaStream_t stream) {
+  constexpr int smem = 5 * Geo<HD>::kTileBytes;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_band_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return set_error(-5, cudaGetErrorString(e));
+    configured = true;
+  }
+  const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
+  dim3 grid((T + kBQ - 1) / kBQ, H, B);
+  attn_band_kernel<HD><<<grid, 128, smem, stream>>>(static_cast<const __nv_bfloat16*>(qkv),
+                                                   static_cast<__nv_bfloat16*>(out), T, H, wl, wr, mask,
+                                                   scale_log2);
+  OSUDIT_CHECK_LAUNCH();
+  return 0;
 }
 
 bool attn_window_applicable(int T, int head_dim, int w_left, int w_right, const uint8_t* mask);
@@ -229,21 +266,19 @@ using namespace osudit;
 
 extern "C" int osudit_attn_band(const void* qkv, void* out, int B, int T, int H, int head_dim,
                                 int w_left, int w_right, const uint8_t* mask, int algo, void* stream) {
-  if (head_dim != 64) return set_error(-1, "attn_band: only head_dim 64 is implemented");
+  if (head_dim != 64 && head_dim != 72)
+    return set_error(-1, "attn_band: head_dim must be 64 (DiT-S/B/L) or 72 (DiT-XL)");
   if (B <= 0 || T <= 0 || H <= 0) return set_error(-1, "attn_band: bad shape");
+  if (B > 65535 || H > 65535) return set_error(-1, "attn_band: batch/heads exceed the launch grid");
   if (w_left < 0 || w_left > T) w_left = T;
   if (w_right < 0 || w_right > T) w_right = T;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool window_ok = attn_window_applicable(T, head_dim, w_left, w_right, mask);
   if (algo == OSUDIT_ATTN_TCGEN05 && !window_ok)
     return set_error(-1, "attn_band: tcgen05 window kernel needs head_dim 64, no generic mask, and "
                          "a band within +-128 or T <= 256");
   if (algo != OSUDIT_ATTN_MMA_SYNC && window_ok)
-    return attn_window_launch(qkv, out, B, T, H, w_left, w_right, static_cast<cudaStream_t>(stream));
-  const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(head_dim));
-  dim3 grid((T + kBQ - 1) / kBQ, H, B);
-  attn_band_kernel<64><<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), T, H, w_left,
-      w_right, mask, scale_log2);
-  OSUDIT_CHECK_LAUNCH();
-  return 0;
+    return attn_window_launch(qkv, out, B, T, H, w_left, w_right, st);
+  if (head_dim == 64) return launch_band<64>(qkv, out, B, T, H, w_left, w_right, mask, st);
+  return launch_band<72>(qkv, out, B, T, H, w_left, w_right, mask, st);
 }

@@ -79,6 +79,22 @@ def test_gemm_split_bf16_three_segments_is_fp32_accurate():
 
 
 # -------------------------------------------------------------------------- attention
+@pytest.mark.parametrize("B,T,H,W", [(2, 300, 2, 128), (1, 128, 3, None), (2, 2048, 1, 128), (1, 513, 2, 64)])
+def test_attn_head_dim_72(B, T, H, W):
+    """DiT-XL heads (1152 / 16 = 72, reference models.py:410-412): zero-padded to 80 in shared memory."""
+    hd = 72
+    qkv = bf(torch.randn(B * T, 3 * H * hd, device=DEV, generator=torch.Generator(device=DEV).manual_seed(T)))
+    out = torch.full((B * T, H * hd), float("nan"), device=DEV, dtype=torch.bfloat16)
+    if W is None:
+        ops.attn_band(qkv, out, B, T, H, hd)
+        ref = _attn_ref(qkv, B, T, H, hd, None)
+    else:
+        ops.attn_band(qkv, out, B, T, H, hd, W - 1, W)
+        ref = _attn_ref(qkv, B, T, H, hd, synth.band_mask(T, W).to(DEV))
+    assert not bool(torch.isnan(out.float()).any())
+    assert rel(out.float(), ref) < 6e-3
+
+
 def _attn_ref(qkv, B, T, H, hd, mask):
     D = H * hd
     q, k, v = (z.reshape(B, T, H, hd).transpose(1, 2).float() for z in qkv.reshape(B, T, 3 * D).split(D, -1))

@@ -56,6 +56,26 @@ def test_forward_matches_oracle(name, T, W):
 
 
 @torch.no_grad()
+def test_xl_width_and_head_dim_72():
+    """DiT-XL geometry (hidden 1152, 16 heads of 72) at reduced depth so the CPU oracle stays fast."""
+    import models
+    shape = odit.DiTShape(depth=3, hidden=1152, heads=16)
+    sd = odit.init_state_dict(shape, seed=5)
+    m = models.DiT(depth=3, hidden_size=1152, num_heads=16, num_classes=52670, context_size=144)
+    m.load_state_dict(sd, strict=True)
+    m = m.to(DEV).eval()
+    T = 200
+    z, o, c, y = synth.sampling_batch(1, T, seed=2)
+    t = torch.tensor([700, 3])
+    mask = synth.band_mask(T, 64)
+    ref = odit.forward(sd, 16, z, t, o, c, y, mask)
+    out = m(*to_dev(z, t), o=o.to(DEV), c=c.to(DEV), y=y.to(DEV), attn_mask=mask.to(DEV))
+    e = rel(out[:, :2], ref[:, :2])
+    print(f"XL-width depth 3: eps rel-L2 {e:.2e}")
+    assert e < EPS_TOL
+
+
+@torch.no_grad()
 def test_forward_with_cfg_matches_oracle():
     shape, sd, m = build("DiT-B")
     T, n = 256, 2
