@@ -31,6 +31,7 @@ import torch  # noqa: E402
 
 MODEL, N_BEATMAPS, SEQ, STEPS_DIFF, CFG, BAND = "DiT-B", 64, 2048, 100, 1.5, 128
 METRIC = "beatmaps/sec DiT-B 100-step CFG sampling"
+NCU_GEMM_TRAFFIC_GB = 1.57  # ncu --set full, profiles/r01_summary.md: (1.558 + 0.762 + 1.962 + 2.003) / 4
 UNIT = "beatmaps/s"
 
 
@@ -266,7 +267,8 @@ def kernel_roofline(model, diffusion, zd, od, cd, yd, mask_d, device):
     ach = fl / (ms / 1e3) / 1e12
     return {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (QKV, out-proj, fc1+GELU, fc2 launches)",
             "achieved": round(ach, 1), "peak": tf_peak, "unit": "TFLOP/s", "frac": round(ach / tf_peak, 4),
-            "traffic": None, "peak_source": src, "launches_timed": n,
+            "traffic": NCU_GEMM_TRAFFIC_GB, "traffic_unit": "GB per launch (dram read+write, mean of the QKV/out-proj/"
+            "fc1/fc2 launches in profiles/r01_summary.md; algorithmic 1.56)", "peak_source": src, "launches_timed": n,
             "avg_launch_ms": round(ms / max(n, 1), 4), "share_of_step": round(ms / step_ms, 3),
             "per_shape_tflops": {k: round(v[0] / (v[1] / 1e3) / 1e12, 1) for k, v in by_shape.items()},
             "hbm_kernel": {"kernel": "ln_modulate_kernel", "bound": "hbm",
