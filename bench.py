@@ -121,6 +121,7 @@ def run_native(args, rank, world, local_rank):
     dist = None
     if world > 1:
         import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=device)
     model = build_native(device)
     diffusion = create_diffusion(str(STEPS_DIFF), noise_schedule="squaredcos_cap_v2")
