@@ -53,17 +53,66 @@ int osudit_gemm_bf16(int nseg, const void* const* a, const int64_t* lda, const v
 #define OSUDIT_ATTN_AUTO 0
 #define OSUDIT_ATTN_MMA_SYNC 1
 #define OSUDIT_ATTN_TCGEN05 2
+/* lse (optional, fp32 [B, H, T]): log2-domain log-sum-exp of every row, saved for the backward;
+ * requesting it selects the mma.sync kernel. */
 int osudit_attn_band(const void* qkv, void* out, int B, int T, int H, int head_dim, int w_left,
-                     int w_right, const uint8_t* mask, int algo, void* stream);
+                     int w_right, const uint8_t* mask, int algo, float* lse, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Backward pass (training, train.py:249-257: autograd through DiT.forward under the loss of
+ * gaussian_diffusion.py:785-874).  Data- and weight-gradient GEMMs reuse osudit_gemm_bf16 on
+ * operands transposed by osudit_transpose_bf16.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* dqkv (bf16 [B*T, 3*H*64]) from dout (bf16 [B*T, H*64]), the forward's qkv / out / lse.
+ * delta is fp32 [B, H, T] scratch.  Band semantics as in osudit_attn_band; head_dim 64 only. */
+int osudit_attn_band_bwd(const void* qkv, const void* out, const void* dout, const float* lse,
+                         float* delta, void* dqkv, int B, int T, int H, int head_dim, int w_left,
+                         int w_right, void* stream);
+
+/* out[cols, out_ld] (bf16, out_ld >= rows: pad the GEMM K dimension to a multiple of 8) = in[rows, cols]^T;
+ * in is bf16, or fp32 when in_is_f32. */
+int osudit_transpose_bf16(const void* in, void* out, int64_t rows, int64_t cols, int64_t out_ld, int in_is_f32,
+                          void* stream);
+
+/* backward == 0: out = gelu_tanh(pre);  backward == 1: out = dy * gelu_tanh'(pre).  bf16, n % 8 == 0. */
+int osudit_gelu(const void* pre, const void* dy, void* out, int64_t n, int backward, void* stream);
+
+/* out[N] (fp32, ACCUMULATED: caller zeroes) += column sums of in[rows, N] (bf16 or fp32): bias grads. */
+int osudit_colsum(const void* in, int in_is_f32, int64_t rows, int N, float* out, void* stream);
+
+/* Backward of x_out = x + gate[b] * y (models.py:161-163,172):
+ * dy (bf16) = gate[b] * dx;  dgate[b] (fp32, accumulated) += sum_t dx * y. */
+int osudit_gate_residual_bwd(const float* dx, const void* y, const float* gate, float* dgate,
+                             int64_t mod_ld, int B, int T, int D, void* dy, void* stream);
+
+/* Backward of h = LayerNorm(x) * (1 + scale[b]) + shift[b] (models.py:12-13,160,173):
+ * dshift[b], dscale[b] accumulated (fp32); dx written (accumulate == 0) or added to (== 1). */
+int osudit_ln_modulate_bwd(const float* x, const void* dh, const float* scale, float* dshift,
+                           float* dscale, int64_t mod_ld, int B, int T, int D, float* dx,
+                           int accumulate, void* stream);
+
+/* Backward of FinalLayer (models.py:192-196) given dout fp32 [B,4,T] and x = the layer's input
+ * (last gated residual already applied): dw [4,D], dbias [4], dshift/dscale accumulated; dx written. */
+int osudit_final_layer_bwd(const float* x, const float* dout, const float* shift, const float* scale,
+                           float* dshift, float* dscale, int64_t mod_ld, int B, int T, int D,
+                           const float* w, float* dw, float* dbias, float* dx, void* stream);
+
+/* dcond[r] = ds[r] * SiLU'(a[r] + table[y[r]]);  dtable[y[r]] += dcond[r] when dtable != NULL
+ * (dense label-embedding gradient, models.py:73). */
+int osudit_silu_bwd(const float* a, const float* table, const int64_t* y, const float* ds, int64_t rows,
+                    int D, float* dcond, float* dtable, void* stream);
 
 /* x (fp32 [rows, D], in place) += gate[b] * branch (bf16 [rows, D]) when branch != NULL, then
  * h (bf16 [rows, D]) = LayerNorm(x) * (1 + scale[b]) + shift[b], b = row / T.
  * gate/shift/scale point at column 0 of their chunk in the adaLN output, `mod_ld` floats per batch
  * row.  Replaces modulate(norm(x), shift, scale) and the gated residual adds
  * (models.py:12-13,160-163,172-174). */
+/* x_out (optional): write the updated residual there instead of in place (training keeps every
+ * LayerNorm input for the backward). */
 int osudit_ln_modulate(float* x, const void* branch, const float* gate, const float* shift,
                        const float* scale, int64_t mod_ld, int64_t rows, int T, int D, void* h,
-                       void* stream);
+                       float* x_out, void* stream);
 
 /* FinalLayer (models.py:192-196) fused with the last gated residual add and the output transpose
  * (models.py:323-324): out fp32 [B, out_channels, T]; w fp32 [out_channels, D]. */
@@ -114,6 +163,17 @@ int osudit_cfg_combine(const float* model_out, int B, int T, float cfg_scale, fl
 /* q_sample (gaussian_diffusion.py:231-247): out = sqrt_acp[t] x0 + sqrt_1m_acp[t] noise. */
 int osudit_q_sample(const float* x0, const float* noise, const int64_t* t, const float* sqrt_acp,
                     const float* sqrt_1m_acp, int B, int64_t per_row, float* out, void* stream);
+
+/* Training loss values and gradient (gaussian_diffusion.py:785-874, EPSILON + LEARNED_RANGE):
+ * term_main[b] = mean |noise-eps| (use_l1) or (noise-eps)^2, term_vb[b] = VB term in bits (eps
+ * detached), dmodel_out [B,4,T] = d(term_main + term_vb)[b] / d model_out[b].  coef_table as in
+ * osudit_diffusion_step; t indexes it. */
+int osudit_diffusion_loss(const float* model_out, const float* x0, const float* x_t, const float* noise,
+                          const int64_t* t, const float* coef_table, int B, int T, int use_l1,
+                          float* term_main, float* term_vb, float* dmodel_out, void* stream);
+
+/* out[b, :] = in[b, :] * g[b] (chain rule through the per-sample loss). */
+int osudit_scale_rows(const float* in, const float* g, int B, int64_t per_row, float* out, void* stream);
 
 #ifdef __cplusplus
 }

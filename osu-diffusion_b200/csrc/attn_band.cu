@@ -58,7 +58,8 @@ __device__ __forceinline__ void load_tile_async(uint8_t* s, const __nv_bfloat16*
 template <int HD>
 __global__ void __launch_bounds__(128)
 attn_band_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int T, int H,
-                 int wl, int wr, const uint8_t* __restrict__ mask, float scale_log2) {
+                 int wl, int wr, const uint8_t* __restrict__ mask, float scale_log2,
+                 float* __restrict__ lse) {
   using G = Geo<HD>;
   extern __shared__ __align__(128) uint8_t smem_attn[];
   uint8_t* sQ = smem_attn;
@@ -219,6 +220,8 @@ attn_band_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
     l += __shfl_xor_sync(0xffffffffu, l, 2);
     const float inv = 1.0f / l;  // 0/0 -> NaN for a fully masked row, as the reference's softmax
     const int r = warp * 16 + (lane >> 2) + rr * 8;
+    if (lse != nullptr && (lane & 3) == 0 && q0 + r < T)  // log2-domain log-sum-exp, for the backward
+      lse[(static_cast<int64_t>(b) * H + h) * T + q0 + r] = m_run[rr] * scale_log2 + log2f(l);
 #pragma unroll
     for (int db = 0; db < G::kChunks; ++db) {
       const uint32_t v = pack_bf16(o_acc[db][2 * rr] * inv, o_acc[db][2 * rr + 1] * inv);
@@ -239,7 +242,7 @@ attn_band_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
 
 template <int HD>
 static int launch_band(const void* qkv, void* out, int B, int T, int H, int wl, int wr,
-                       const uint8_t* mask, cudaStream_t stream) {
+                       const uint8_t* mask, float* lse, cudaStream_t stream) {
   constexpr int smem = 5 * Geo<HD>::kTileBytes;
   static bool configured = false;
   if (!configured) {
@@ -251,9 +254,313 @@ static int launch_band(const void* qkv, void* out, int B, int T, int H, int wl, 
   dim3 grid((T + kBQ - 1) / kBQ, H, B);
   attn_band_kernel<HD><<<grid, 128, smem, stream>>>(static_cast<const __nv_bfloat16*>(qkv),
                                                    static_cast<__nv_bfloat16*>(out), T, H, wl, wr, mask,
-                                                   scale_log2);
+                                                   scale_log2, lse);
   OSUDIT_CHECK_LAUNCH();
   return 0;
+}
+
+
+// =================================================================================== backward
+// Flash-style backward of the same attention (autograd of nn.MultiheadAttention's core in the
+// reference, train.py:257).  P is recomputed from Q, K and the forward's log2-domain LSE:
+//   P = exp2(S * scale_log2 - lse),  delta = rowsum(dO * O),  dS = P * (dP - delta),
+//   dQ = scale * dS K,  dK = scale * dS^T Q,  dV = P^T dO,  with dP = dO V^T.
+// Two kernels so that no atomics are needed: one owns 64 queries (dQ), one owns 64 keys (dK, dV).
+// head_dim 64 only (the training configurations of BASELINE.json use DiT-B / DiT-L).
+
+// delta[b, h, t] = sum_d dO[b, t, h, d] * O[b, t, h, d]
+__global__ void __launch_bounds__(256)
+attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout,
+                  float* __restrict__ delta, int64_t rows, int T, int H) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int64_t b = row / T, t = row - b * T;
+  for (int h = 0; h < H; ++h) {
+    const int64_t off = (row * H + h) * 64 + lane * 2;
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(o + off));
+    const float2 d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dout + off));
+    float v = a.x * d.x + a.y * d.y;
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+    if (lane == 0) delta[(b * H + h) * T + t] = v;
+  }
+}
+
+template <int HD>
+__global__ void __launch_bounds__(128)
+attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout,
+                   const float* __restrict__ lse, const float* __restrict__ delta,
+                   __nv_bfloat16* __restrict__ dqkv, int T, int H, int wl, int wr, float scale_log2,
+                   float scale) {
+  using G = Geo<HD>;
+  static_assert(HD == 64, "backward is built for head_dim 64");
+  extern __shared__ __align__(128) uint8_t smem_attn[];
+  uint8_t* sQ = smem_attn;
+  uint8_t* sdO = sQ + G::kTileBytes;
+  uint8_t* sK[2] = {sQ + 2 * G::kTileBytes, sQ + 3 * G::kTileBytes};
+  uint8_t* sV[2] = {sQ + 4 * G::kTileBytes, sQ + 5 * G::kTileBytes};
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q0 = blockIdx.x * kBQ, h = blockIdx.y, b = blockIdx.z;
+  const int D = H * HD;
+  const int64_t ld = 3 * static_cast<int64_t>(D);
+  const __nv_bfloat16* gq = qkv + static_cast<int64_t>(b) * T * ld + h * HD;
+  const __nv_bfloat16* gk = gq + D;
+  const __nv_bfloat16* gv = gq + 2 * D;
+  const __nv_bfloat16* gdo = dout + static_cast<int64_t>(b) * T * D + h * HD;
+
+  const int kt_lo = max(0, q0 - wl) / kBKV;
+  const int kt_hi = min(T - 1, min(q0 + kBQ - 1, T - 1) + wr) / kBKV;
+  load_tile_async<HD>(sQ, gq, ld, q0, T, tid);
+  load_tile_async<HD>(sdO, gdo, D, q0, T, tid);
+  load_tile_async<HD>(sK[0], gk, ld, kt_lo * kBKV, T, tid);
+  load_tile_async<HD>(sV[0], gv, ld, kt_lo * kBKV, T, tid);
+  cp_async_commit();
+
+  float dq[HD / 8][4];
+#pragma unroll
+  for (int i = 0; i < HD / 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
+  uint32_t qf[HD / 16][4], dof[HD / 16][4];
+  const int qrow[2] = {q0 + warp * 16 + (lane >> 2), q0 + warp * 16 + (lane >> 2) + 8};
+  float row_lse[2], row_delta[2];
+#pragma unroll
+  for (int rr = 0; rr < 2; ++rr) {
+    const bool ok = qrow[rr] < T;
+    const int64_t idx = (static_cast<int64_t>(b) * H + h) * T + (ok ? qrow[rr] : 0);
+    row_lse[rr] = ok ? lse[idx] : 0.f;
+    row_delta[rr] = ok ? delta[idx] : 0.f;
+  }
+
+  for (int kt = kt_lo; kt <= kt_hi; ++kt) {
+    const int buf = (kt - kt_lo) & 1;
+    if (kt < kt_hi) {
+      load_tile_async<HD>(sK[buf ^ 1], gk, ld, (kt + 1) * kBKV, T, tid);
+      load_tile_async<HD>(sV[buf ^ 1], gv, ld, (kt + 1) * kBKV, T, tid);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    if (kt == kt_lo) {
+#pragma unroll
+      for (int ks = 0; ks < HD / 16; ++ks) {
+        const int r = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+        const int ch = ks * 2 + (lane >> 4);
+        ldmatrix_x4(qf[ks], smem_u32(sQ) + G::off(r, ch));
+        ldmatrix_x4(dof[ks], smem_u32(sdO) + G::off(r, ch));
+      }
+    }
+    float s[kBKV / 8][4], dp[kBKV / 8][4];
+#pragma unroll
+    for (int nb = 0; nb < kBKV / 8; ++nb) {
+      s[nb][0] = s[nb][1] = s[nb][2] = s[nb][3] = 0.f;
+      dp[nb][0] = dp[nb][1] = dp[nb][2] = dp[nb][3] = 0.f;
+    }
+    const uint32_t sk = smem_u32(sK[buf]), sv = smem_u32(sV[buf]);
+#pragma unroll
+    for (int ks = 0; ks < HD / 16; ++ks) {
+#pragma unroll
+      for (int nb = 0; nb < kBKV / 8; nb += 2) {
+        uint32_t kf[4], vf[4];
+        const int r = nb * 8 + (lane & 7) + ((lane >> 4) & 1) * 8;
+        const int ch = ks * 2 + ((lane >> 3) & 1);
+        ldmatrix_x4(kf, sk + G::off(r, ch));
+        ldmatrix_x4(vf, sv + G::off(r, ch));
+        mma_bf16_16816(s[nb], qf[ks], kf[0], kf[1]);
+        mma_bf16_16816(s[nb + 1], qf[ks], kf[2], kf[3]);
+        mma_bf16_16816(dp[nb], dof[ks], vf[0], vf[1]);
+        mma_bf16_16816(dp[nb + 1], dof[ks], vf[2], vf[3]);
+      }
+    }
+    const int k0 = kt * kBKV;
+#pragma unroll
+    for (int nb = 0; nb < kBKV / 8; ++nb) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int q = qrow[e >> 1];
+        const int k = k0 + nb * 8 + (lane & 3) * 2 + (e & 1);
+        const bool ok = (k < T) && (q < T) && (k - q >= -wl) && (k - q <= wr);
+        const float p = ok ? exp2f(s[nb][e] * scale_log2 - row_lse[e >> 1]) : 0.f;
+        s[nb][e] = p * (dp[nb][e] - row_delta[e >> 1]);  // dS
+      }
+    }
+#pragma unroll
+    for (int kk = 0; kk < kBKV / 16; ++kk) {
+      uint32_t pf[4];
+      pf[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
+      pf[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
+      pf[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+      pf[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+      for (int db = 0; db < HD / 8; db += 2) {
+        uint32_t kf[4];
+        const int r = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+        const int ch = db + (lane >> 4);
+        ldmatrix_x4_trans(kf, sk + G::off(r, ch));
+        mma_bf16_16816(dq[db], pf, kf[0], kf[1]);
+        mma_bf16_16816(dq[db + 1], pf, kf[2], kf[3]);
+      }
+    }
+    __syncthreads();
+  }
+  __nv_bfloat16* gdq = dqkv + static_cast<int64_t>(b) * T * ld + h * HD;
+#pragma unroll
+  for (int rr = 0; rr < 2; ++rr) {
+    if (qrow[rr] >= T) continue;
+#pragma unroll
+    for (int db = 0; db < HD / 8; ++db)
+      *reinterpret_cast<uint32_t*>(gdq + static_cast<int64_t>(qrow[rr]) * ld + db * 8 + (lane & 3) * 2) =
+          pack_bf16(dq[db][2 * rr] * scale, dq[db][2 * rr + 1] * scale);
+  }
+}
+
+template <int HD>
+__global__ void __launch_bounds__(128)
+attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout,
+                    const float* __restrict__ lse, const float* __restrict__ delta,
+                    __nv_bfloat16* __restrict__ dqkv, int T, int H, int wl, int wr, float scale_log2,
+                    float scale) {
+  using G = Geo<HD>;
+  static_assert(HD == 64, "backward is built for head_dim 64");
+  extern __shared__ __align__(128) uint8_t smem_attn[];
+  uint8_t* sK = smem_attn;
+  uint8_t* sV = sK + G::kTileBytes;
+  uint8_t* sQ[2] = {sK + 2 * G::kTileBytes, sK + 3 * G::kTileBytes};
+  uint8_t* sdO[2] = {sK + 4 * G::kTileBytes, sK + 5 * G::kTileBytes};
+  float* s_lse = reinterpret_cast<float*>(sK + 6 * G::kTileBytes);  // [2][64]
+  float* s_delta = s_lse + 2 * kBQ;                                 // [2][64]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int k0 = blockIdx.x * kBKV, h = blockIdx.y, b = blockIdx.z;
+  const int D = H * HD;
+  const int64_t ld = 3 * static_cast<int64_t>(D);
+  const __nv_bfloat16* gq = qkv + static_cast<int64_t>(b) * T * ld + h * HD;
+  const __nv_bfloat16* gk = gq + D;
+  const __nv_bfloat16* gv = gq + 2 * D;
+  const __nv_bfloat16* gdo = dout + static_cast<int64_t>(b) * T * D + h * HD;
+  const float* g_lse = lse + (static_cast<int64_t>(b) * H + h) * T;
+  const float* g_delta = delta + (static_cast<int64_t>(b) * H + h) * T;
+
+  // queries that may see any of these keys: key - query in [-wl, wr]
+  const int qt_lo = max(0, k0 - wr) / kBQ;
+  const int qt_hi = min(T - 1, min(k0 + kBKV - 1, T - 1) + wl) / kBQ;
+  auto load_stats = [&](int buf, int qbase) {
+    if (tid < kBQ) {
+      const int q = qbase + tid;
+      s_lse[buf * kBQ + tid] = q < T ? g_lse[q] : 0.f;
+      s_delta[buf * kBQ + tid] = q < T ? g_delta[q] : 0.f;
+    }
+  };
+  load_tile_async<HD>(sK, gk, ld, k0, T, tid);
+  load_tile_async<HD>(sV, gv, ld, k0, T, tid);
+  load_tile_async<HD>(sQ[0], gq, ld, qt_lo * kBQ, T, tid);
+  load_tile_async<HD>(sdO[0], gdo, D, qt_lo * kBQ, T, tid);
+  cp_async_commit();
+  load_stats(0, qt_lo * kBQ);
+
+  float dk[HD / 8][4], dv[HD / 8][4];
+#pragma unroll
+  for (int i = 0; i < HD / 8; ++i) {
+    dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f;
+    dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f;
+  }
+  uint32_t kfr[HD / 16][4], vfr[HD / 16][4];
+  const int krow[2] = {k0 + warp * 16 + (lane >> 2), k0 + warp * 16 + (lane >> 2) + 8};
+
+  for (int qt = qt_lo; qt <= qt_hi; ++qt) {
+    const int buf = (qt - qt_lo) & 1;
+    if (qt < qt_hi) {
+      load_tile_async<HD>(sQ[buf ^ 1], gq, ld, (qt + 1) * kBQ, T, tid);
+      load_tile_async<HD>(sdO[buf ^ 1], gdo, D, (qt + 1) * kBQ, T, tid);
+      cp_async_commit();
+      load_stats(buf ^ 1, (qt + 1) * kBQ);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    if (qt == qt_lo) {
+#pragma unroll
+      for (int ks = 0; ks < HD / 16; ++ks) {
+        const int r = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+        const int ch = ks * 2 + (lane >> 4);
+        ldmatrix_x4(kfr[ks], smem_u32(sK) + G::off(r, ch));
+        ldmatrix_x4(vfr[ks], smem_u32(sV) + G::off(r, ch));
+      }
+    }
+    // S^T[key, query] and dP^T[key, query]
+    float st[kBQ / 8][4], dpt[kBQ / 8][4];
+#pragma unroll
+    for (int nb = 0; nb < kBQ / 8; ++nb) {
+      st[nb][0] = st[nb][1] = st[nb][2] = st[nb][3] = 0.f;
+      dpt[nb][0] = dpt[nb][1] = dpt[nb][2] = dpt[nb][3] = 0.f;
+    }
+    const uint32_t sq = smem_u32(sQ[buf]), sdo = smem_u32(sdO[buf]);
+#pragma unroll
+    for (int ks = 0; ks < HD / 16; ++ks) {
+#pragma unroll
+      for (int nb = 0; nb < kBQ / 8; nb += 2) {
+        uint32_t qfr[4], dofr[4];
+        const int r = nb * 8 + (lane & 7) + ((lane >> 4) & 1) * 8;
+        const int ch = ks * 2 + ((lane >> 3) & 1);
+        ldmatrix_x4(qfr, sq + G::off(r, ch));
+        ldmatrix_x4(dofr, sdo + G::off(r, ch));
+        mma_bf16_16816(st[nb], kfr[ks], qfr[0], qfr[1]);
+        mma_bf16_16816(st[nb + 1], kfr[ks], qfr[2], qfr[3]);
+        mma_bf16_16816(dpt[nb], vfr[ks], dofr[0], dofr[1]);
+        mma_bf16_16816(dpt[nb + 1], vfr[ks], dofr[2], dofr[3]);
+      }
+    }
+    const int qb = qt * kBQ;
+    uint32_t pf[kBQ / 16][4], dsf[kBQ / 16][4];
+#pragma unroll
+    for (int nb = 0; nb < kBQ / 8; ++nb) {
+      float pv[4], dsv[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int k = krow[e >> 1];
+        const int qc = nb * 8 + (lane & 3) * 2 + (e & 1);
+        const int q = qb + qc;
+        const bool ok = (k < T) && (q < T) && (k - q >= -wl) && (k - q <= wr);
+        const float p = ok ? exp2f(st[nb][e] * scale_log2 - s_lse[buf * kBQ + qc]) : 0.f;
+        pv[e] = p;
+        dsv[e] = p * (dpt[nb][e] - s_delta[buf * kBQ + qc]);
+      }
+      // accumulator blocks (2kk, 2kk+1) form the A fragment of k-step kk
+      pf[nb >> 1][(nb & 1) * 2 + 0] = pack_bf16(pv[0], pv[1]);
+      pf[nb >> 1][(nb & 1) * 2 + 1] = pack_bf16(pv[2], pv[3]);
+      dsf[nb >> 1][(nb & 1) * 2 + 0] = pack_bf16(dsv[0], dsv[1]);
+      dsf[nb >> 1][(nb & 1) * 2 + 1] = pack_bf16(dsv[2], dsv[3]);
+    }
+#pragma unroll
+    for (int kk = 0; kk < kBQ / 16; ++kk) {
+#pragma unroll
+      for (int db = 0; db < HD / 8; db += 2) {
+        uint32_t dofr[4], qfr[4];
+        const int r = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+        const int ch = db + (lane >> 4);
+        ldmatrix_x4_trans(dofr, sdo + G::off(r, ch));
+        ldmatrix_x4_trans(qfr, sq + G::off(r, ch));
+        mma_bf16_16816(dv[db], pf[kk], dofr[0], dofr[1]);
+        mma_bf16_16816(dv[db + 1], pf[kk], dofr[2], dofr[3]);
+        mma_bf16_16816(dk[db], dsf[kk], qfr[0], qfr[1]);
+        mma_bf16_16816(dk[db + 1], dsf[kk], qfr[2], qfr[3]);
+      }
+    }
+    __syncthreads();
+  }
+  __nv_bfloat16* gdk = dqkv + static_cast<int64_t>(b) * T * ld + D + h * HD;
+  __nv_bfloat16* gdv = gdk + D;
+#pragma unroll
+  for (int rr = 0; rr < 2; ++rr) {
+    if (krow[rr] >= T) continue;
+#pragma unroll
+    for (int db = 0; db < HD / 8; ++db) {
+      const int64_t off = static_cast<int64_t>(krow[rr]) * ld + db * 8 + (lane & 3) * 2;
+      *reinterpret_cast<uint32_t*>(gdk + off) = pack_bf16(dk[db][2 * rr] * scale, dk[db][2 * rr + 1] * scale);
+      *reinterpret_cast<uint32_t*>(gdv + off) = pack_bf16(dv[db][2 * rr], dv[db][2 * rr + 1]);
+    }
+  }
 }
 
 bool attn_window_applicable(int T, int head_dim, int w_left, int w_right, const uint8_t* mask);
@@ -265,7 +572,8 @@ int attn_window_launch(const void* qkv, void* out, int B, int T, int H, int w_le
 using namespace osudit;
 
 extern "C" int osudit_attn_band(const void* qkv, void* out, int B, int T, int H, int head_dim,
-                                int w_left, int w_right, const uint8_t* mask, int algo, void* stream) {
+                                int w_left, int w_right, const uint8_t* mask, int algo, float* lse,
+                                void* stream) {
   if (head_dim != 64 && head_dim != 72)
     return set_error(-1, "attn_band: head_dim must be 64 (DiT-S/B/L) or 72 (DiT-XL)");
   if (B <= 0 || T <= 0 || H <= 0) return set_error(-1, "attn_band: bad shape");
@@ -273,12 +581,48 @@ extern "C" int osudit_attn_band(const void* qkv, void* out, int B, int T, int H,
   if (w_left < 0 || w_left > T) w_left = T;
   if (w_right < 0 || w_right > T) w_right = T;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const bool window_ok = attn_window_applicable(T, head_dim, w_left, w_right, mask);
+  const bool window_ok = lse == nullptr && attn_window_applicable(T, head_dim, w_left, w_right, mask);
   if (algo == OSUDIT_ATTN_TCGEN05 && !window_ok)
     return set_error(-1, "attn_band: tcgen05 window kernel needs head_dim 64, no generic mask, and "
                          "a band within +-128 or T <= 256");
   if (algo != OSUDIT_ATTN_MMA_SYNC && window_ok)
     return attn_window_launch(qkv, out, B, T, H, w_left, w_right, st);
-  if (head_dim == 64) return launch_band<64>(qkv, out, B, T, H, w_left, w_right, mask, st);
-  return launch_band<72>(qkv, out, B, T, H, w_left, w_right, mask, st);
+  if (head_dim == 64) return launch_band<64>(qkv, out, B, T, H, w_left, w_right, mask, lse, st);
+  return launch_band<72>(qkv, out, B, T, H, w_left, w_right, mask, lse, st);
+}
+
+extern "C" int osudit_attn_band_bwd(const void* qkv, const void* out, const void* dout, const float* lse,
+                                    float* delta, void* dqkv, int B, int T, int H, int head_dim,
+                                    int w_left, int w_right, void* stream) {
+  if (head_dim != 64) return set_error(-1, "attn_band_bwd: only head_dim 64 is implemented");
+  if (B <= 0 || T <= 0 || H <= 0 || B > 65535 || H > 65535) return set_error(-1, "attn_band_bwd: bad shape");
+  if (w_left < 0 || w_left > T) w_left = T;
+  if (w_right < 0 || w_right > T) w_right = T;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t rows = static_cast<int64_t>(B) * T;
+  attn_delta_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, st>>>(
+      static_cast<const __nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(dout), delta, rows, T, H);
+  OSUDIT_CHECK_LAUNCH();
+  constexpr int smem_dq = 6 * Geo<64>::kTileBytes;
+  constexpr int smem_dkv = 6 * Geo<64>::kTileBytes + 4 * kBQ * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_dq_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dq);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_bwd_dkv_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dkv);
+    if (e != cudaSuccess) return set_error(-5, cudaGetErrorString(e));
+    configured = true;
+  }
+  const float scale = 1.0f / sqrtf(static_cast<float>(head_dim));
+  const float scale_log2 = 1.4426950408889634f * scale;
+  dim3 grid((T + kBQ - 1) / kBQ, H, B);
+  attn_bwd_dq_kernel<64><<<grid, 128, smem_dq, st>>>(
+      static_cast<const __nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(dout), lse, delta,
+      static_cast<__nv_bfloat16*>(dqkv), T, H, w_left, w_right, scale_log2, scale);
+  OSUDIT_CHECK_LAUNCH();
+  attn_bwd_dkv_kernel<64><<<grid, 128, smem_dkv, st>>>(
+      static_cast<const __nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(dout), lse, delta,
+      static_cast<__nv_bfloat16*>(dqkv), T, H, w_left, w_right, scale_log2, scale);
+  OSUDIT_CHECK_LAUNCH();
+  return 0;
 }

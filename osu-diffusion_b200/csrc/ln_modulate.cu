@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(256)
 ln_modulate_kernel(float* __restrict__ x, const __nv_bfloat16* __restrict__ y,
                    const float* __restrict__ gate, const float* __restrict__ shift,
                    const float* __restrict__ scale, int64_t mod_ld, int64_t rows, int T,
-                   __nv_bfloat16* __restrict__ h) {
+                   __nv_bfloat16* __restrict__ h, float* __restrict__ x_out) {
   constexpr int D = NV * 128;
   const int lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
@@ -81,9 +81,10 @@ ln_modulate_kernel(float* __restrict__ x, const __nv_bfloat16* __restrict__ y,
   float4 v[NV];
   load_row_update<NV, kHasBranch>(v, xrow, kHasBranch ? y + row * D : nullptr,
                                   kHasBranch ? gate + b * mod_ld : nullptr, lane);
-  if (kHasBranch) {
+  if (kHasBranch) {  // updated residual: in place, or to x_out when the caller keeps x (training)
+    float* xw = x_out != nullptr ? x_out + row * D : xrow;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) *reinterpret_cast<float4*>(xrow + (lane + 32 * i) * 4) = v[i];
+    for (int i = 0; i < NV; ++i) *reinterpret_cast<float4*>(xw + (lane + 32 * i) * 4) = v[i];
   }
   float mean, rstd;
   row_stats<NV>(v, mean, rstd);
@@ -174,9 +175,9 @@ template <int NV, bool HB>
 struct LnLauncher {
   static int run(float* x, const __nv_bfloat16* y, const float* gate, const float* shift,
                  const float* scale, int64_t mod_ld, int64_t rows, int T, __nv_bfloat16* h,
-                 cudaStream_t st) {
+                 float* x_out, cudaStream_t st) {
     const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
-    ln_modulate_kernel<NV, HB><<<grid, 256, 0, st>>>(x, y, gate, shift, scale, mod_ld, rows, T, h);
+    ln_modulate_kernel<NV, HB><<<grid, 256, 0, st>>>(x, y, gate, shift, scale, mod_ld, rows, T, h, x_out);
     OSUDIT_CHECK_LAUNCH();
     return 0;
   }
@@ -201,13 +202,13 @@ using namespace osudit;
 
 extern "C" int osudit_ln_modulate(float* x, const void* branch, const float* gate,
                                   const float* shift, const float* scale, int64_t mod_ld,
-                                  int64_t rows, int T, int D, void* h, void* stream) {
+                                  int64_t rows, int T, int D, void* h, float* x_out, void* stream) {
   if (rows <= 0 || T <= 0) return set_error(-1, "ln_modulate: bad shape");
   if ((branch == nullptr) != (gate == nullptr))
     return set_error(-1, "ln_modulate: branch and gate must be given together");
   return dispatch_nv<LnLauncher>(D, branch != nullptr, x, static_cast<const __nv_bfloat16*>(branch),
                                  gate, shift, scale, mod_ld, rows, T,
-                                 static_cast<__nv_bfloat16*>(h), static_cast<cudaStream_t>(stream));
+                                 static_cast<__nv_bfloat16*>(h), x_out, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int osudit_final_layer(float* x, const void* branch, const float* gate,

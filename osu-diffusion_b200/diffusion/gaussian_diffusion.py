@@ -257,6 +257,25 @@ class GaussianDiffusion:
 
     # -------------------------------------------------------------------------- training
     def training_losses(self, model, x_start, t, model_kwargs=None, noise=None):
-        raise NotImplementedError(
-            "training_losses: the native training path (backward kernels) is not built yet; "
-            "round 1 covers the sampling path (DESIGN.md, scope)")
+        """Per-sample training losses (reference :785-874) for EPSILON + LEARNED_RANGE with MSE or L1:
+        returns {"loss", "mse"|"l1", "vb"}, each of shape (B,), "loss" differentiable w.r.t. the
+        model parameters.  q_sample, the loss arithmetic, its gradient and the model's forward and
+        backward all run in libosudit; the VB term sees a detached eps as in :833."""
+        self._require_native_config()
+        if self.loss_type not in (LossType.MSE, LossType.L1):
+            raise NotImplementedError("only the MSE / L1 (+VB) losses create_diffusion builds by default are native")
+        from osudit.train import LossFunction
+
+        x_start = x_start.float().contiguous()
+        t = t.long().contiguous()
+        if noise is None:
+            noise = th.randn_like(x_start)
+        noise = noise.float().contiguous()
+        tb = self._tables(x_start.device)
+        x_t = ops.q_sample(x_start, noise, t, tb["sqrt_acp"], tb["sqrt_1m_acp"], th.empty_like(x_start))
+        model_output = model(x_t, tb["tmap"][t], **(model_kwargs or {}))
+        B, C = x_t.shape[:2]
+        assert model_output.shape == (B, C * 2, *x_t.shape[2:])
+        use_l1 = self.loss_type == LossType.L1
+        loss, main, vb = LossFunction.apply(model_output.float(), x_start, x_t, noise, t, tb["step"], use_l1)
+        return {"loss": loss, ("l1" if use_l1 else "mse"): main, "vb": vb}

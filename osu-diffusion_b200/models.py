@@ -112,6 +112,7 @@ class DiT(nn.Module):
         self.final_layer = _FinalLayer(hidden_size, self.out_channels)
         self.initialize_weights()
         self._engine = None
+        self._train_weights = None
 
     def initialize_weights(self):
         """Same distributions as models.py:275-304 (xavier-uniform Linears with zero bias,
@@ -140,7 +141,7 @@ class DiT(nn.Module):
         new = cls.__new__(cls)
         memo[id(self)] = new
         for k, v in self.__dict__.items():
-            new.__dict__[k] = None if k == "_engine" else copy.deepcopy(v, memo)
+            new.__dict__[k] = None if k in ("_engine", "_train_weights") else copy.deepcopy(v, memo)
         return new
 
     def engine(self) -> DiTEngine:
@@ -158,16 +159,30 @@ class DiT(nn.Module):
             if not v.is_cuda:
                 raise RuntimeError(f"DiT.forward: `{name}` is on {v.device}; the native path runs on "
                                    "CUDA only and has no CPU fallback")
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError(
-                "backward through the native DiT path is not built yet (round 1 covers sampling); "
-                "call under torch.no_grad()")
         return self.engine().forward(x.float().contiguous(), t.long().contiguous(),
                                      o.float().contiguous(), c.float().contiguous(),
                                      self._labels(y.long()).contiguous(), attn_mask, x_rows)
 
+    def _needs_grad(self):
+        return torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+
     def forward(self, x, t, o, c, y, attn_mask=None):
-        """x (N,2,T), t (N,), o (N,T) ms, c (N,E,T), y (N,) -> (N,4,T); models.py:306-325."""
+        """x (N,2,T), t (N,), o (N,T) ms, c (N,E,T), y (N,) -> (N,4,T); models.py:306-325.
+
+        With autograd on (train.py:249-257) the call becomes one autograd node whose backward is the
+        native schedule in osudit/train.py; under no_grad it is the inference schedule."""
+        if self._needs_grad():
+            from osudit.train import DiTFunction, TrainWeights
+            for name, v in (("x", x), ("t", t), ("o", o), ("c", c), ("y", y)):
+                if not v.is_cuda:
+                    raise RuntimeError(f"DiT.forward: `{name}` is on {v.device}; the native path runs "
+                                       "on CUDA only and has no CPU fallback")
+            if self._train_weights is None:
+                self._train_weights = TrainWeights()
+            tw = self._train_weights.refresh(self)
+            return DiTFunction.apply(self, tw, x.detach().float().contiguous(), t.long().contiguous(),
+                                     o.float().contiguous(), c.float().contiguous(),
+                                     self._labels(y.long()).contiguous(), attn_mask, *self.parameters())
         return self._raw_forward(x, t, o, c, y, attn_mask).clone()
 
     def forward_with_cfg(self, x, t, o, c, y, cfg_scale, attn_mask=None):

@@ -22,8 +22,18 @@ SIGNATURES = {
     "osudit_version": [],
     "osudit_last_error": [],
     "osudit_gemm_bf16": [_I, _P, _P, _P, _P, _P, _L, _L, _P, _I, _P, _L, _P],
-    "osudit_attn_band": [_P, _P, _I, _I, _I, _I, _I, _I, _P, _I, _P],
-    "osudit_ln_modulate": [_P, _P, _P, _P, _P, _L, _L, _I, _I, _P, _P],
+    "osudit_attn_band": [_P, _P, _I, _I, _I, _I, _I, _I, _P, _I, _P, _P],
+    "osudit_attn_band_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "osudit_transpose_bf16": [_P, _P, _L, _L, _L, _I, _P],
+    "osudit_gelu": [_P, _P, _P, _L, _I, _P],
+    "osudit_colsum": [_P, _I, _L, _I, _P, _P],
+    "osudit_gate_residual_bwd": [_P, _P, _P, _P, _L, _I, _I, _I, _P, _P],
+    "osudit_ln_modulate_bwd": [_P, _P, _P, _P, _P, _L, _I, _I, _I, _P, _I, _P],
+    "osudit_final_layer_bwd": [_P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _P, _P, _P, _P, _P],
+    "osudit_silu_bwd": [_P, _P, _P, _P, _L, _I, _P, _P, _P],
+    "osudit_diffusion_loss": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P],
+    "osudit_scale_rows": [_P, _P, _I, _L, _P, _P],
+    "osudit_ln_modulate": [_P, _P, _P, _P, _P, _L, _L, _I, _I, _P, _P, _P],
     "osudit_final_layer": [_P, _P, _P, _P, _P, _L, _L, _I, _I, _P, _P, _I, _P, _P],
     "osudit_embed_xoc": [_P, _P, _P, _P, _F, _F, _I, _I, _I, _I, _P, _P, _P],
     "osudit_timestep_features": [_P, _P, _I, _P, _P, _P],

@@ -58,12 +58,14 @@ def gemm(a_segs, b_segs, bias, epilogue: int, out: torch.Tensor) -> torch.Tensor
 ATTN_AUTO, ATTN_MMA_SYNC, ATTN_TCGEN05 = 0, 1, 2
 
 
-def attn_band(qkv, out, B, T, H, head_dim, w_left=-1, w_right=-1, mask=None, algo=ATTN_AUTO):
+def attn_band(qkv, out, B, T, H, head_dim, w_left=-1, w_right=-1, mask=None, algo=ATTN_AUTO, lse=None):
     mp = _chk(mask, torch.uint8, "attn.mask") if mask is not None else None
     lib = _lib.load()
     _lib.check(lib.osudit_attn_band(_chk(qkv, torch.bfloat16, "attn.qkv"),
                                     _chk(out, torch.bfloat16, "attn.out"), B, T, H, head_dim,
-                                    w_left, w_right, mp, algo, _stream()), "osudit_attn_band")
+                                    w_left, w_right, mp, algo,
+                                    _chk(lse, torch.float32, "attn.lse") if lse is not None else None,
+                                    _stream()), "osudit_attn_band")
     return out
 
 
@@ -71,7 +73,7 @@ def _off(t: torch.Tensor, col: int) -> int:
     return t.data_ptr() + col * t.element_size()
 
 
-def ln_modulate(x, branch, mod, gate_col, shift_col, scale_col, T, h):
+def ln_modulate(x, branch, mod, gate_col, shift_col, scale_col, T, h, x_out=None):
     """x fp32 [rows,D] (+= gate*branch in place), h bf16 = LN(x)*(1+scale)+shift; the three chunks
     live at columns gate_col/shift_col/scale_col of `mod` fp32 [B, mod_ld]."""
     rows, D = x.shape
@@ -81,7 +83,9 @@ def ln_modulate(x, branch, mod, gate_col, shift_col, scale_col, T, h):
     gp = _off(mod, gate_col) if branch is not None else None
     _lib.check(lib.osudit_ln_modulate(_chk(x, torch.float32, "ln.x"), bp, gp, _off(mod, shift_col),
                                       _off(mod, scale_col), mod.stride(0), rows, T, D,
-                                      _chk(h, torch.bfloat16, "ln.h"), _stream()), "osudit_ln_modulate")
+                                      _chk(h, torch.bfloat16, "ln.h"),
+                                      _chk(x_out, torch.float32, "ln.x_out") if x_out is not None else None,
+                                      _stream()), "osudit_ln_modulate")
     return h
 
 
@@ -174,4 +178,117 @@ def q_sample(x0, noise, t, sqrt_acp, sqrt_1m_acp, out):
                                    _chk(t, torch.int64, "q.t"), _chk(sqrt_acp, torch.float32, "q.a"),
                                    _chk(sqrt_1m_acp, torch.float32, "q.b"), B, x0.numel() // B,
                                    _chk(out, torch.float32, "q.out"), _stream()), "osudit_q_sample")
+    return out
+
+
+# ------------------------------------------------------------------------------ backward ops
+def _pad8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+def transpose(a: torch.Tensor) -> torch.Tensor:
+    """[R, C] (bf16 or fp32) -> bf16 [C, pad8(R)] with zero padding: a K-major GEMM operand whose
+    K dimension is the (padded) row count of `a`."""
+    R, C = a.shape
+    ld = _pad8(R)
+    out = torch.empty(C, ld, dtype=torch.bfloat16, device=a.device)
+    if ld != R:
+        out[:, R:].zero_()
+    lib = _lib.load()
+    is_f32 = a.dtype == torch.float32
+    _lib.check(lib.osudit_transpose_bf16(_chk(a, torch.float32 if is_f32 else torch.bfloat16, "transpose.in"),
+                                         out.data_ptr(), R, C, ld, int(is_f32), _stream()), "osudit_transpose_bf16")
+    return out
+
+
+def gelu(pre, out, dy=None):
+    lib = _lib.load()
+    _lib.check(lib.osudit_gelu(_chk(pre, torch.bfloat16, "gelu.pre"),
+                               _chk(dy, torch.bfloat16, "gelu.dy") if dy is not None else None,
+                               _chk(out, torch.bfloat16, "gelu.out"), pre.numel(), int(dy is not None), _stream()),
+               "osudit_gelu")
+    return out
+
+
+def colsum(a, out):
+    """out[N] (fp32) += column sums of a[rows, N]."""
+    rows, N = a.shape
+    lib = _lib.load()
+    is_f32 = a.dtype == torch.float32
+    _lib.check(lib.osudit_colsum(_chk(a, torch.float32 if is_f32 else torch.bfloat16, "colsum.in"), int(is_f32),
+                                 rows, N, _chk(out, torch.float32, "colsum.out"), _stream()), "osudit_colsum")
+    return out
+
+
+def gate_residual_bwd(dx, y, mod, dmod, gate_col, B, T, dy):
+    D = dx.shape[1]
+    lib = _lib.load()
+    _lib.check(lib.osudit_gate_residual_bwd(_chk(dx, torch.float32, "grb.dx"), _chk(y, torch.bfloat16, "grb.y"),
+                                            _off(mod, gate_col), _off(dmod, gate_col), mod.stride(0), B, T, D,
+                                            _chk(dy, torch.bfloat16, "grb.dy"), _stream()),
+               "osudit_gate_residual_bwd")
+    return dy
+
+
+def ln_modulate_bwd(x, dh, mod, dmod, shift_col, scale_col, B, T, dx, accumulate):
+    D = x.shape[1]
+    lib = _lib.load()
+    _lib.check(lib.osudit_ln_modulate_bwd(_chk(x, torch.float32, "lnb.x"), _chk(dh, torch.bfloat16, "lnb.dh"),
+                                          _off(mod, scale_col), _off(dmod, shift_col), _off(dmod, scale_col),
+                                          mod.stride(0), B, T, D, _chk(dx, torch.float32, "lnb.dx"),
+                                          int(accumulate), _stream()), "osudit_ln_modulate_bwd")
+    return dx
+
+
+def final_layer_bwd(x, dout, mod, dmod, shift_col, scale_col, B, T, w, dw, dbias, dx):
+    D = x.shape[1]
+    lib = _lib.load()
+    _lib.check(lib.osudit_final_layer_bwd(_chk(x, torch.float32, "fb.x"), _chk(dout, torch.float32, "fb.dout"),
+                                          _off(mod, shift_col), _off(mod, scale_col), _off(dmod, shift_col),
+                                          _off(dmod, scale_col), mod.stride(0), B, T, D,
+                                          _chk(w, torch.float32, "fb.w"), _chk(dw, torch.float32, "fb.dw"),
+                                          _chk(dbias, torch.float32, "fb.dbias"), _chk(dx, torch.float32, "fb.dx"),
+                                          _stream()), "osudit_final_layer_bwd")
+
+
+def silu_bwd(a, ds, dcond, table=None, y=None, dtable=None):
+    rows, D = a.shape
+    lib = _lib.load()
+    _lib.check(lib.osudit_silu_bwd(_chk(a, torch.float32, "sb.a"),
+                                   _chk(table, torch.float32, "sb.table") if table is not None else None,
+                                   _chk(y, torch.int64, "sb.y") if y is not None else None,
+                                   _chk(ds, torch.float32, "sb.ds"), rows, D, _chk(dcond, torch.float32, "sb.dcond"),
+                                   _chk(dtable, torch.float32, "sb.dtable") if dtable is not None else None,
+                                   _stream()), "osudit_silu_bwd")
+    return dcond
+
+
+def attn_band_bwd(qkv, out, dout, lse, dqkv, B, T, H, head_dim, w_left=-1, w_right=-1):
+    delta = torch.empty(B, H, T, dtype=torch.float32, device=qkv.device)
+    lib = _lib.load()
+    _lib.check(lib.osudit_attn_band_bwd(_chk(qkv, torch.bfloat16, "ab.qkv"), _chk(out, torch.bfloat16, "ab.out"),
+                                        _chk(dout, torch.bfloat16, "ab.dout"), _chk(lse, torch.float32, "ab.lse"),
+                                        delta.data_ptr(), _chk(dqkv, torch.bfloat16, "ab.dqkv"), B, T, H, head_dim,
+                                        w_left, w_right, _stream()), "osudit_attn_band_bwd")
+    return dqkv
+
+
+def diffusion_loss(model_out, x0, x_t, noise, t, coef_table, use_l1, term_main, term_vb, dmodel_out):
+    B, _, T = x0.shape
+    lib = _lib.load()
+    _lib.check(lib.osudit_diffusion_loss(_chk(model_out, torch.float32, "loss.out"), _chk(x0, torch.float32, "loss.x0"),
+                                         _chk(x_t, torch.float32, "loss.x_t"), _chk(noise, torch.float32, "loss.noise"),
+                                         _chk(t, torch.int64, "loss.t"), _chk(coef_table, torch.float32, "loss.coef"),
+                                         B, T, int(bool(use_l1)), _chk(term_main, torch.float32, "loss.main"),
+                                         _chk(term_vb, torch.float32, "loss.vb"),
+                                         _chk(dmodel_out, torch.float32, "loss.dout"), _stream()),
+               "osudit_diffusion_loss")
+
+
+def scale_rows(a, g, out):
+    B = a.shape[0]
+    lib = _lib.load()
+    _lib.check(lib.osudit_scale_rows(_chk(a, torch.float32, "sr.in"), _chk(g, torch.float32, "sr.g"), B,
+                                     a.numel() // B, _chk(out, torch.float32, "sr.out"), _stream()),
+               "osudit_scale_rows")
     return out

@@ -1,0 +1,263 @@
+"""Training-time forward (activations kept) and backward of the DiT, as one autograd node.
+
+The reference gets its gradients from PyTorch autograd over `DiT.forward` (train.py:249-257).  Here the
+whole model is a single `torch.autograd.Function` whose forward and backward are fixed schedules of
+libosudit launches: autograd, DDP and the optimizer see the same leaf parameters and receive fp32
+gradients for them, nothing else runs in torch.
+
+Data-gradient GEMMs use transposed weight copies, weight-gradient GEMMs use transposed activations
+(`ops.transpose` pads the token dimension to a multiple of 8 with zeros); both then run on the same
+tcgen05 GEMM as the forward.  Gradients flow in bf16 between GEMMs and in fp32 along the residual
+stream and into every parameter.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+from .engine import FREQ_SEQ, FREQ_T, classify_mask
+
+
+def _bf(p):
+    return p.detach().to(torch.bfloat16).contiguous()
+
+
+def _wt(p):
+    """Transposed bf16 copy of an nn.Linear weight [out, in] -> [in, out] (the B operand of dgrad)."""
+    return p.detach().t().to(torch.bfloat16).contiguous()
+
+
+class TrainWeights:
+    """bf16 / split-bf16 / transposed copies of the parameters, rebuilt when a version changes."""
+
+    def __init__(self):
+        self.sig = None
+
+    def refresh(self, model):
+        sig = tuple((p.data_ptr(), p._version) for p in model.parameters())
+        if sig == self.sig:
+            return self
+        self.first_w = ops.split_bf16(model.xoc_embedder.mlp[0].weight)
+        self.t0_w = ops.split_bf16(model.t_embedder.mlp[0].weight)
+        self.t2_w = ops.split_bf16(model.t_embedder.mlp[2].weight)
+        self.t2_wt = _wt(model.t_embedder.mlp[2].weight)
+        mods = [b.adaLN_modulation[1] for b in model.blocks] + [model.final_layer.adaLN_modulation[1]]
+        mod_w = torch.cat([m.weight.detach() for m in mods], 0)
+        self.mod_w = ops.split_bf16(mod_w)
+        self.mod_wt = _wt(mod_w)
+        self.mod_b = torch.cat([m.bias.detach() for m in mods], 0).float().contiguous()
+        self.blocks = []
+        for blk in model.blocks:
+            self.blocks.append(dict(
+                qkv_w=_bf(blk.attn.in_proj_weight), qkv_wt=_wt(blk.attn.in_proj_weight),
+                out_w=_bf(blk.attn.out_proj.weight), out_wt=_wt(blk.attn.out_proj.weight),
+                fc1_w=_bf(blk.mlp.fc1.weight), fc1_wt=_wt(blk.mlp.fc1.weight),
+                fc2_w=_bf(blk.mlp.fc2.weight), fc2_wt=_wt(blk.mlp.fc2.weight)))
+        self.sig = sig
+        return self
+
+
+def _gemm3(a_hi, a_lo, w, bias, out):
+    w_hi, w_lo = w
+    return ops.gemm([a_hi, a_lo, a_hi], [w_hi, w_hi, w_lo], bias, ops.EPI_F32, out)
+
+
+def _e(*shape, dtype=torch.bfloat16, device=None):
+    return torch.empty(*shape, dtype=dtype, device=device)
+
+
+def forward_train(model, tw: TrainWeights, x, t, o, c, y, attn_mask):
+    """DiT.forward (models.py:306-325) keeping what the backward needs. Returns (out [B,4,T], saved)."""
+    B, T = o.shape
+    D, H, depth = model.hidden_size, model.num_heads, len(model.blocks)
+    hd, E, dev = D // H, model.context_size, o.device
+    if hd != 64:
+        raise NotImplementedError("the native backward covers head_dim 64 (DiT-S/B/L); DiT-XL training is not built")
+    rows = B * T
+    spec = classify_mask(attn_mask, T)
+    if spec.generic is not None:
+        raise NotImplementedError("training with a generic attention mask is not built (None or a band only)")
+    eng = model.engine()
+    f32 = lambda p: p.detach().float().contiguous()  # noqa: E731
+    S = dict(B=B, T=T, spec=spec, y=y)
+
+    kin = 3 * FREQ_SEQ + E
+    a_hi, a_lo = _e(rows, kin, device=dev), _e(rows, kin, device=dev)
+    pf = [float(v) for v in model.xoc_embedder.playfield_size.detach().cpu()]
+    ops.embed_xoc(x, o, c, eng.freqs(FREQ_SEQ // 2, dev), pf[0], pf[1], B, a_hi, a_lo)
+    xa = _e(rows, D, dtype=torch.float32, device=dev)
+    _gemm3(a_hi, a_lo, tw.first_w, f32(model.xoc_embedder.mlp[0].bias), xa)
+    S["a_hi"] = a_hi
+
+    # conditioning: mod = Linear_all(SiLU(t_emb + y_emb))
+    tf_hi, tf_lo = _e(B, FREQ_T, device=dev), _e(B, FREQ_T, device=dev)
+    ops.timestep_features(t, eng.freqs(FREQ_T // 2, dev), tf_hi, tf_lo)
+    h1t = _e(B, D, dtype=torch.float32, device=dev)
+    _gemm3(tf_hi, tf_lo, tw.t0_w, f32(model.t_embedder.mlp[0].bias), h1t)
+    s1_hi, s1_lo = _e(B, D, device=dev), _e(B, D, device=dev)
+    ops.silu_split(h1t, s1_hi, s1_lo)
+    temb = _e(B, D, dtype=torch.float32, device=dev)
+    _gemm3(s1_hi, s1_lo, tw.t2_w, f32(model.t_embedder.mlp[2].bias), temb)
+    table = f32(model.y_embedder.embedding_table.weight)
+    c_hi, c_lo = _e(B, D, device=dev), _e(B, D, device=dev)
+    ops.silu_split(temb, c_hi, c_lo, table=table, y=y)
+    mod = _e(B, (6 * depth + 2) * D, dtype=torch.float32, device=dev)
+    _gemm3(c_hi, c_lo, tw.mod_w, tw.mod_b, mod)
+    S.update(tf_hi=tf_hi, h1t=h1t, s1_hi=s1_hi, temb=temb, table=table, c_hi=c_hi, mod=mod)
+
+    saved_blocks = []
+    y2 = None
+    for i, (blk, bw) in enumerate(zip(model.blocks, tw.blocks)):
+        base = 6 * D * i
+        h1 = _e(rows, D, device=dev)
+        if i == 0:
+            ops.ln_modulate(xa, None, mod, 0, base, base + D, T, h1)
+        else:
+            xa_new = _e(rows, D, dtype=torch.float32, device=dev)
+            ops.ln_modulate(xb, y2, mod, base - D, base, base + D, T, h1, x_out=xa_new)
+            xa = xa_new
+        qkv = _e(rows, 3 * D, device=dev)
+        ops.gemm([h1], [bw["qkv_w"]], f32(blk.attn.in_proj_bias), ops.EPI_BF16, qkv)
+        att = _e(rows, D, device=dev)
+        lse = _e(B, H, T, dtype=torch.float32, device=dev)
+        ops.attn_band(qkv, att, B, T, H, hd, spec.w_left, spec.w_right, None, ops.ATTN_MMA_SYNC, lse=lse)
+        y1 = _e(rows, D, device=dev)
+        ops.gemm([att], [bw["out_w"]], f32(blk.attn.out_proj.bias), ops.EPI_BF16, y1)
+        xb = _e(rows, D, dtype=torch.float32, device=dev)
+        h2 = _e(rows, D, device=dev)
+        ops.ln_modulate(xa, y1, mod, base + 2 * D, base + 3 * D, base + 4 * D, T, h2, x_out=xb)
+        pre = _e(rows, bw["fc1_w"].shape[0], device=dev)
+        ops.gemm([h2], [bw["fc1_w"]], f32(blk.mlp.fc1.bias), ops.EPI_BF16, pre)
+        u = ops.gelu(pre, torch.empty_like(pre))
+        y2 = _e(rows, D, device=dev)
+        ops.gemm([u], [bw["fc2_w"]], f32(blk.mlp.fc2.bias), ops.EPI_BF16, y2)
+        saved_blocks.append(dict(xa=xa, h1=h1, qkv=qkv, att=att, lse=lse, y1=y1, xb=xb, h2=h2, pre=pre, u=u, y2=y2))
+    fbase = 6 * D * depth
+    xf = _e(rows, D, dtype=torch.float32, device=dev)
+    ops.ln_modulate(xb, y2, mod, fbase - D, fbase, fbase + D, T, _e(rows, D, device=dev), x_out=xf)
+    out = _e(B, 4, T, dtype=torch.float32, device=dev)
+    ops.final_layer(xf, None, mod, 0, fbase, fbase + D, T, f32(model.final_layer.linear.weight),
+                    f32(model.final_layer.linear.bias), out)
+    S.update(blocks=saved_blocks, xf=xf)
+    return out, S
+
+
+def _wgrad(dy_t, x_t, out_shape, dev):
+    """dW[N, K] = dY^T[N, rows] . X^T[K, rows]^T with both operands already transposed."""
+    return ops.gemm([dy_t], [x_t], None, ops.EPI_F32, torch.empty(out_shape, dtype=torch.float32, device=dev))
+
+
+def backward_train(model, tw: TrainWeights, S, dout):
+    """Gradients of every trainable parameter, in `model.parameters()` order (None where frozen)."""
+    B, T, spec = S["B"], S["T"], S["spec"]
+    D, H, depth = model.hidden_size, model.num_heads, len(model.blocks)
+    rows, dev, mod = B * T, dout.device, S["mod"]
+    z32 = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)  # noqa: E731
+    grads = {}
+    dmod = z32(B, mod.shape[1])
+    dx = _e(rows, D, dtype=torch.float32, device=dev)
+
+    fbase = 6 * D * depth
+    fl = model.final_layer
+    grads[fl.linear.weight], grads[fl.linear.bias] = z32(4, D), z32(4)
+    ops.final_layer_bwd(S["xf"], dout.contiguous(), mod, dmod, fbase, fbase + D, B, T,
+                        fl.linear.weight.detach().float().contiguous(), grads[fl.linear.weight],
+                        grads[fl.linear.bias], dx)
+
+    for i in reversed(range(depth)):
+        blk, bw, sv = model.blocks[i], tw.blocks[i], S["blocks"][i]
+        base = 6 * D * i
+        hidden = sv["pre"].shape[1]
+        # ---- MLP branch: x_out = xb + gate_mlp * y2
+        dy2 = ops.gate_residual_bwd(dx, sv["y2"], mod, dmod, base + 5 * D, B, T, _e(rows, D, device=dev))
+        dy2_t = ops.transpose(dy2)
+        grads[blk.mlp.fc2.weight] = _wgrad(dy2_t, ops.transpose(sv["u"]), (D, hidden), dev)
+        grads[blk.mlp.fc2.bias] = ops.colsum(dy2, z32(D))
+        du = ops.gemm([dy2], [bw["fc2_wt"]], None, ops.EPI_BF16, _e(rows, hidden, device=dev))
+        dpre = ops.gelu(sv["pre"], du, dy=du)  # in place over du
+        grads[blk.mlp.fc1.weight] = _wgrad(ops.transpose(dpre), ops.transpose(sv["h2"]), (hidden, D), dev)
+        grads[blk.mlp.fc1.bias] = ops.colsum(dpre, z32(hidden))
+        dh2 = ops.gemm([dpre], [bw["fc1_wt"]], None, ops.EPI_BF16, _e(rows, D, device=dev))
+        ops.ln_modulate_bwd(sv["xb"], dh2, mod, dmod, base + 3 * D, base + 4 * D, B, T, dx, True)
+        # ---- attention branch: xb = xa + gate_msa * y1
+        dy1 = ops.gate_residual_bwd(dx, sv["y1"], mod, dmod, base + 2 * D, B, T, dy2)  # reuse buffer
+        grads[blk.attn.out_proj.weight] = _wgrad(ops.transpose(dy1), ops.transpose(sv["att"]), (D, D), dev)
+        grads[blk.attn.out_proj.bias] = ops.colsum(dy1, z32(D))
+        datt = ops.gemm([dy1], [bw["out_wt"]], None, ops.EPI_BF16, dh2)  # reuse buffer
+        dqkv = ops.attn_band_bwd(sv["qkv"], sv["att"], datt, sv["lse"], _e(rows, 3 * D, device=dev), B, T, H,
+                                 D // H, spec.w_left, spec.w_right)
+        grads[blk.attn.in_proj_weight] = _wgrad(ops.transpose(dqkv), ops.transpose(sv["h1"]), (3 * D, D), dev)
+        grads[blk.attn.in_proj_bias] = ops.colsum(dqkv, z32(3 * D))
+        dh1 = ops.gemm([dqkv], [bw["qkv_wt"]], None, ops.EPI_BF16, datt)  # reuse buffer
+        ops.ln_modulate_bwd(sv["xa"], dh1, mod, dmod, base, base + D, B, T, dx, True)
+
+    # ---- first layer: x0 = a W^T + b  (no gradient to the inputs)
+    first = model.xoc_embedder.mlp[0]
+    grads[first.weight] = _wgrad(ops.transpose(dx), ops.transpose(S["a_hi"]), tuple(first.weight.shape), dev)
+    grads[first.bias] = ops.colsum(dx, z32(D))
+
+    # ---- conditioning path: mod = s Wmod^T + bmod, s = SiLU(temb + table[y])
+    dmod_bf, _ = ops.split_bf16(dmod, need_lo=False)
+    dmod_t = ops.transpose(dmod)
+    gw = _wgrad(dmod_t, ops.transpose(S["c_hi"]), (mod.shape[1], D), dev)
+    gb = ops.colsum(dmod, z32(mod.shape[1]))
+    mods = [b.adaLN_modulation[1] for b in model.blocks] + [fl.adaLN_modulation[1]]
+    r0 = 0
+    for m in mods:
+        n = m.weight.shape[0]
+        grads[m.weight], grads[m.bias] = gw[r0:r0 + n], gb[r0:r0 + n]
+        r0 += n
+    ds = ops.gemm([dmod_bf], [tw.mod_wt], None, ops.EPI_F32, _e(B, D, dtype=torch.float32, device=dev))
+    table_p = model.y_embedder.embedding_table.weight
+    grads[table_p] = z32(*table_p.shape)
+    dcond = ops.silu_bwd(S["temb"], ds, torch.empty_like(ds), table=S["table"], y=S["y"], dtable=grads[table_p])
+    # t-MLP: temb = SiLU(tf W0^T + b0) W2^T + b2
+    t0, t2 = model.t_embedder.mlp[0], model.t_embedder.mlp[2]
+    dcond_t = ops.transpose(dcond)
+    grads[t2.weight] = _wgrad(dcond_t, ops.transpose(S["s1_hi"]), (D, D), dev)
+    grads[t2.bias] = ops.colsum(dcond, z32(D))
+    dcond_bf, _ = ops.split_bf16(dcond, need_lo=False)
+    ds1 = ops.gemm([dcond_bf], [tw.t2_wt], None, ops.EPI_F32, torch.empty_like(ds))
+    dh1t = ops.silu_bwd(S["h1t"], ds1, torch.empty_like(ds1))
+    grads[t0.weight] = _wgrad(ops.transpose(dh1t), ops.transpose(S["tf_hi"]), (D, FREQ_T), dev)
+    grads[t0.bias] = ops.colsum(dh1t, z32(D))
+    return [grads.get(p) if p.requires_grad else None for p in model.parameters()]
+
+
+class DiTFunction(torch.autograd.Function):
+    """out = DiT(x, t, o, c, y) with parameter gradients from the native backward."""
+
+    @staticmethod
+    def forward(ctx, model, tw, x, t, o, c, y, attn_mask, *params):
+        out, saved = forward_train(model, tw, x, t, o, c, y, attn_mask)
+        ctx.model, ctx.tw, ctx.saved = model, tw, saved
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        with torch.no_grad():
+            grads = backward_train(ctx.model, ctx.tw, ctx.saved, dout.float())
+        ctx.saved = None
+        return (None,) * 8 + tuple(grads)
+
+
+class LossFunction(torch.autograd.Function):
+    """training_losses' arithmetic (gaussian_diffusion.py:822-870): values + d loss / d model_out."""
+
+    @staticmethod
+    def forward(ctx, model_out, x0, x_t, noise, t, coef, use_l1):
+        B = x0.shape[0]
+        main = torch.empty(B, dtype=torch.float32, device=x0.device)
+        vb = torch.empty_like(main)
+        dunit = torch.empty_like(model_out)
+        ops.diffusion_loss(model_out.contiguous(), x0, x_t, noise, t, coef, use_l1, main, vb, dunit)
+        ctx.save_for_backward(dunit)
+        loss = main + vb  # B-element add; everything per datapoint happened in the kernel
+        ctx.mark_non_differentiable(main, vb)
+        return loss, main, vb
+
+    @staticmethod
+    def backward(ctx, g_loss, g_main, g_vb):
+        (dunit,) = ctx.saved_tensors
+        g = g_loss.contiguous().float()
+        return ops.scale_rows(dunit, g, torch.empty_like(dunit)), None, None, None, None, None, None

@@ -1,0 +1,226 @@
+"""Training path parity: every backward kernel against torch autograd (fp32, on the GPU), then the
+whole `training_losses` forward + backward against the CPU oracle's autograd."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import diffusion as odiff  # noqa: E402
+from oracle import dit as odit  # noqa: E402
+from osudit import ops, synth  # noqa: E402
+
+DEV = "cuda"
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def bf(t):
+    return t.to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("R,C", [(64, 64), (100, 72), (7, 528), (4096, 768), (3, 4608)])
+@pytest.mark.parametrize("f32", [False, True])
+def test_transpose(R, C, f32):
+    a = torch.randn(R, C, device=DEV)
+    if not f32:
+        a = bf(a)
+    out = ops.transpose(a)
+    assert out.shape == (C, (R + 7) // 8 * 8)
+    assert torch.equal(out[:, :R], bf(a).t())
+    assert float(out[:, R:].abs().sum()) == 0.0
+
+
+def test_gelu_forward_backward():
+    pre = bf(torch.randn(64, 512, device=DEV) * 2)
+    dy = bf(torch.randn(64, 512, device=DEV))
+    x = pre.float().requires_grad_()
+    y = torch.nn.functional.gelu(x, approximate="tanh")
+    y.backward(dy.float())
+    assert rel(ops.gelu(pre, torch.empty_like(pre)).float(), y) < 3e-3
+    assert rel(ops.gelu(pre, torch.empty_like(pre), dy=dy).float(), x.grad) < 4e-3
+
+
+@pytest.mark.parametrize("f32", [False, True])
+def test_colsum(f32):
+    a = torch.randn(1000, 776, device=DEV)
+    if not f32:
+        a = bf(a)
+    out = ops.colsum(a, torch.zeros(776, device=DEV))
+    assert rel(out, a.float().sum(0)) < 1e-5
+
+
+@pytest.mark.parametrize("D", [384, 768, 1024])
+def test_gate_residual_and_ln_modulate_backward(D):
+    B, T = 3, 50
+    rows = B * T
+    x = (torch.randn(rows, D, device=DEV) * 1.5 + 0.3).requires_grad_()
+    y = bf(torch.randn(rows, D, device=DEV))
+    yf = y.float().requires_grad_()
+    mod = (torch.randn(B, 6 * D, device=DEV) * 0.3).requires_grad_()
+    rep = lambda m: m.repeat_interleave(T, 0)  # noqa: E731
+    x2 = x + rep(mod[:, 2 * D:3 * D]) * yf
+    h = torch.nn.functional.layer_norm(x2, (D,), eps=1e-6) * (1 + rep(mod[:, D:2 * D])) + rep(mod[:, :D])
+    dh = bf(torch.randn(rows, D, device=DEV))
+    dx_up = torch.randn(rows, D, device=DEV)  # gradient arriving along the residual stream
+    (h * dh.float()).sum().backward(retain_graph=True)
+    (x2 * dx_up).sum().backward()
+    # native: LN backward accumulates into the incoming residual gradient, then the gated residual
+    dmod = torch.zeros_like(mod)
+    dx = dx_up.clone()
+    ops.ln_modulate_bwd(x2.detach(), dh, mod.detach(), dmod, 0, D, B, T, dx, True)
+    dy = ops.gate_residual_bwd(dx, y, mod.detach(), dmod, 2 * D, B, T, torch.empty_like(y))
+    assert rel(dx, x.grad) < 1e-4
+    assert rel(dy.float(), yf.grad) < 4e-3
+    assert rel(dmod[:, :D], mod.grad[:, :D]) < 1e-4            # shift
+    assert rel(dmod[:, D:2 * D], mod.grad[:, D:2 * D]) < 1e-4  # scale
+    assert rel(dmod[:, 2 * D:3 * D], mod.grad[:, 2 * D:3 * D]) < 1e-4  # gate
+    assert float(dmod[:, 3 * D:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("D", [384, 768])
+def test_final_layer_backward(D):
+    B, T = 2, 37
+    rows = B * T
+    x = torch.randn(rows, D, device=DEV).requires_grad_()
+    mod = (torch.randn(B, 2 * D, device=DEV) * 0.3).requires_grad_()
+    w = (torch.randn(4, D, device=DEV) * 0.05).requires_grad_()
+    bias = torch.randn(4, device=DEV).requires_grad_()
+    rep = lambda m: m.repeat_interleave(T, 0)  # noqa: E731
+    hn = torch.nn.functional.layer_norm(x, (D,), eps=1e-6) * (1 + rep(mod[:, D:])) + rep(mod[:, :D])
+    out = (hn @ w.t() + bias).reshape(B, T, 4).transpose(1, 2)
+    dout = torch.randn(B, 4, T, device=DEV)
+    (out * dout).sum().backward()
+    dmod = torch.zeros_like(mod)
+    dw, db, dx = torch.zeros(4, D, device=DEV), torch.zeros(4, device=DEV), torch.empty(rows, D, device=DEV)
+    ops.final_layer_bwd(x.detach(), dout, mod.detach(), dmod, 0, D, B, T, w.detach(), dw, db, dx)
+    for got, want in ((dx, x.grad), (dw, w.grad), (db, bias.grad), (dmod, mod.grad)):
+        assert rel(got, want) < 1e-4
+
+
+@pytest.mark.parametrize("B,T,H,W", [(2, 128, 3, None), (1, 200, 2, None), (2, 300, 2, 128), (1, 512, 1, 40)])
+def test_attention_backward(B, T, H, W):
+    hd, D = 64, H * 64
+    qkv = bf(torch.randn(B * T, 3 * D, device=DEV))
+    dout = bf(torch.randn(B * T, D, device=DEV))
+    x = qkv.float().requires_grad_()
+    q, k, v = (z.reshape(B, T, H, hd).transpose(1, 2) for z in x.reshape(B, T, 3 * D).split(D, -1))
+    s = q @ k.transpose(-1, -2) / math.sqrt(hd)
+    if W is not None:
+        s = s.masked_fill(synth.band_mask(T, W).to(DEV), float("-inf"))
+    ref = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B * T, D)
+    ref.backward(dout.float())
+    out = torch.empty(B * T, D, device=DEV, dtype=torch.bfloat16)
+    lse = torch.empty(B, H, T, device=DEV)
+    wl, wr = (W - 1, W) if W else (-1, -1)
+    ops.attn_band(qkv, out, B, T, H, hd, wl, wr, None, ops.ATTN_MMA_SYNC, lse=lse)
+    assert rel(out.float(), ref) < 6e-3
+    lse_ref = torch.logsumexp(s, -1) / math.log(2.0)
+    assert float((lse - lse_ref).abs().max()) < 2e-2
+    dqkv = ops.attn_band_bwd(qkv, out, dout, lse, torch.empty_like(qkv), B, T, H, hd, wl, wr)
+    g = x.grad
+    for name, sl in (("dq", slice(0, D)), ("dk", slice(D, 2 * D)), ("dv", slice(2 * D, 3 * D))):
+        e = rel(dqkv[:, sl].float(), g[:, sl])
+        assert e < 1.2e-2, (name, e)
+
+
+@pytest.mark.parametrize("use_l1", [True, False])
+def test_loss_values_and_gradient(use_l1):
+    import numpy as np
+    s = odiff.Schedule("")
+    B, T = 6, 77
+    g = torch.Generator().manual_seed(1)
+    x0 = torch.rand(B, 2, T, generator=g) * 2.2 - 1.1  # some |x0| > 0.999: all three NLL branches
+    noise = torch.randn(B, 2, T, generator=g)
+    t = torch.tensor([0, 0, 1, 500, 999, 250])
+    out = (torch.randn(B, 4, T, generator=g) * 0.8).requires_grad_()
+    terms = odiff.training_losses(s, lambda x_t, tt: out, x0, t, noise, use_l1=use_l1)
+    w = torch.rand(B, generator=g) + 0.5
+    (terms["loss"] * w).sum().backward()
+    table = torch.from_numpy(np.stack([s.log_betas, s.posterior_log_variance_clipped, s.sqrt_recip_alphas_cumprod,
+                                       s.sqrt_recipm1_alphas_cumprod, s.posterior_mean_coef1,
+                                       s.posterior_mean_coef2], 1)).float().to(DEV)
+    x_t = odiff.q_sample(s, x0, t, noise)
+    main, vb = torch.empty(B, device=DEV), torch.empty(B, device=DEV)
+    dunit = torch.empty(B, 4, T, device=DEV)
+    ops.diffusion_loss(out.detach().to(DEV), x0.to(DEV), x_t.to(DEV), noise.to(DEV), t.to(DEV), table, use_l1,
+                       main, vb, dunit)
+    torch.testing.assert_close(main.cpu(), terms["l1" if use_l1 else "mse"].detach(), rtol=2e-5, atol=1e-6)
+    torch.testing.assert_close(vb.cpu(), terms["vb"].detach(), rtol=1e-4, atol=1e-5)
+    grad = ops.scale_rows(dunit, w.to(DEV), torch.empty_like(dunit))
+    assert rel(grad[:, :2], out.grad[:, :2]) < 1e-5
+    assert rel(grad[:, 2:], out.grad[:, 2:]) < 2e-4
+
+
+def _train_setup(name, B, T, seed=1):
+    import models
+    shape = odit.shape_of(name)
+    sd = odit.init_state_dict(shape, seed=seed, zero_init_std=0.05)
+    m = models.DiT_models[name](num_classes=52670, context_size=144, class_dropout_prob=0.2)
+    m.load_state_dict(sd, strict=True)
+    m = m.to(DEV).eval()  # eval: no label dropout, so both sides see the same labels
+    (x, o, c), y = synth.training_batch(B, T, seed=3)
+    g = torch.Generator().manual_seed(5)
+    noise = torch.randn(B, 2, T, generator=g)
+    t = torch.randint(0, 1000, (B,), generator=g)
+    t[0] = 0
+    return shape, sd, m, (x, o, c, y, noise, t)
+
+
+@pytest.mark.parametrize("name,B,T,use_l1", [("DiT-S", 4, 128, True), ("DiT-S", 3, 100, False), ("DiT-B", 2, 128, True)])
+def test_training_losses_and_parameter_gradients(name, B, T, use_l1):
+    from diffusion import create_diffusion
+    shape, sd, m, (x, o, c, y, noise, t) = _train_setup(name, B, T)
+    # oracle: fp32 autograd on CPU
+    sdg = {k: v.clone().requires_grad_(v.is_floating_point() and "playfield" not in k) for k, v in sd.items()}
+    s = odiff.Schedule("")
+    terms_ref = odiff.training_losses(s, lambda x_t, tt: odit.forward(sdg, shape.heads, x_t, tt, o, c, y),
+                                      x, t, noise, use_l1=use_l1)
+    terms_ref["loss"].mean().backward()
+    # native
+    d = create_diffusion("", noise_schedule="squaredcos_cap_v2", use_l1=use_l1)
+    terms = d.training_losses(m, x.to(DEV), t.to(DEV), dict(o=o.to(DEV), c=c.to(DEV), y=y.to(DEV)),
+                              noise=noise.to(DEV))
+    key = "l1" if use_l1 else "mse"
+    assert set(terms) == {"loss", key, "vb"} and terms["loss"].shape == (B,)
+    torch.testing.assert_close(terms[key].detach().cpu(), terms_ref[key].detach(), rtol=5e-3, atol=1e-4)
+    torch.testing.assert_close(terms["vb"].detach().cpu(), terms_ref["vb"].detach(), rtol=2e-2, atol=2e-4)
+    terms["loss"].mean().backward()
+    worst = ("", 0.0)
+    for k, p in m.named_parameters():
+        if not p.requires_grad:
+            assert p.grad is None
+            continue
+        assert p.grad is not None and p.grad.shape == p.shape and p.grad.dtype == torch.float32, k
+        e = rel(p.grad, sdg[k].grad)
+        if e > worst[1]:
+            worst = (k, e)
+        assert e < 5e-2, (k, e)
+    print(f"{name} B={B} T={T}: worst parameter-gradient rel-L2 {worst[1]:.2e} ({worst[0]})")
+
+
+def test_one_optimizer_step_reduces_the_loss():
+    """train.py:249-261 in miniature: fp16-autocast context + GradScaler + AdamW on the native path."""
+    from diffusion import create_diffusion
+    shape, sd, m, (x, o, c, y, noise, t) = _train_setup("DiT-S", 8, 128)
+    m.train()
+    d = create_diffusion("", noise_schedule="squaredcos_cap_v2", use_l1=True)
+    opt = torch.optim.AdamW(m.parameters(), lr=1e-3, weight_decay=0)
+    scaler = torch.amp.GradScaler("cuda")
+    kw = dict(o=o.to(DEV), c=c.to(DEV), y=y.to(DEV))
+    losses = []
+    for _ in range(4):
+        torch.manual_seed(0)  # same label-dropout draw every iteration
+        with torch.autocast(device_type="cuda", dtype=torch.float16):
+            loss = d.training_losses(m, x.to(DEV), t.to(DEV), kw, noise=noise.to(DEV))["loss"].mean()
+        scaler.scale(loss).backward()
+        scaler.step(opt)
+        scaler.update()
+        opt.zero_grad(set_to_none=True)
+        losses.append(float(loss))
+    print("losses", losses)
+    assert all(math.isfinite(v) for v in losses) and losses[-1] < losses[0]
