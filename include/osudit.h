@@ -64,6 +64,12 @@ int osudit_attn_band(const void* qkv, void* out, int B, int T, int H, int head_d
  * operands transposed by osudit_transpose_bf16.
  * ---------------------------------------------------------------------------------------------- */
 
+/* Weight gradient of y = x W^T: out[M,N] (fp32, ACCUMULATED: zero it first) += dy[rows,M]^T . x[rows,N],
+ * both operands read token-major as MN-major tcgen05 operands; the token dimension is split across
+ * CTAs and combined with TMA reduce-add.  ld_* in elements (multiples of 8). */
+int osudit_gemm_wgrad(const void* dy, int64_t ld_dy, const void* x, int64_t ld_x, int64_t rows, int64_t M,
+                      int64_t N, float* out, int64_t ldo, void* stream);
+
 /* dqkv (bf16 [B*T, 3*H*64]) from dout (bf16 [B*T, H*64]), the forward's qkv / out / lse.
  * delta is fp32 [B, H, T] scratch.  Band semantics as in osudit_attn_band; head_dim 64 only. */
 int osudit_attn_band_bwd(const void* qkv, const void* out, const void* dout, const float* lse,

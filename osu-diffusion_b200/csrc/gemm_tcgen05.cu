@@ -42,6 +42,7 @@ struct GemmParams {
   int nseg;
   int M, N;
   int m_tiles, n_tiles;
+  int k_splits, kb_per_split;  // EPI_WGRAD: the K range (token dimension) is split across CTAs
   const float* bias;
 };
 
@@ -85,15 +86,20 @@ __device__ __forceinline__ float gelu_tanh(float x) {
   return __fdividef(x, 1.0f + e);
 }
 
-enum : int { EPI_F32 = 0, EPI_BF16 = 1, EPI_BF16_GELU = 2 };
+// EPI_WGRAD: out[M,N] (fp32, reduce-added) += A[K,M]^T . B[K,N] with BOTH operands token-major
+// (rows = the contraction index): the weight-gradient GEMM dW = dY^T X read straight from dY and X
+// as MN-major UMMA operands, K split across CTAs, partial tiles combined by TMA reduce-add.
+enum : int { EPI_F32 = 0, EPI_BF16 = 1, EPI_BF16_GELU = 2, EPI_WGRAD = 3 };
 
-__host__ __device__ constexpr int epi_threads(int epi) { return epi == EPI_F32 ? 128 : 256; }
+__host__ __device__ constexpr bool epi_is_f32(int epi) { return epi == EPI_F32 || epi == EPI_WGRAD; }
+__host__ __device__ constexpr int epi_threads(int epi) { return epi_is_f32(epi) ? 128 : 256; }
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(64 + epi_threads(EPI), 1)
 gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
   using C = Cfg<BN>;
-  constexpr int kEpiCols = (EPI == EPI_F32) ? 32 : 64;  // 128 bytes of output per row per chunk
+  constexpr int kEpiCols = epi_is_f32(EPI) ? 32 : 64;  // 128 bytes of output per row per chunk
+  constexpr bool kWgrad = EPI == EPI_WGRAD;
   constexpr int kChunks = BN / kEpiCols;
   constexpr int kEpiThreads = epi_threads(EPI);
 
@@ -109,7 +115,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int total_tiles = p.m_tiles * p.n_tiles * (kWgrad ? p.k_splits : 1);  // work items
   int total_kblocks = 0;
   for (int s = 0; s < p.nseg; ++s) total_kblocks += p.kblocks[s];
 
@@ -143,9 +149,28 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int work = blockIdx.x; work < total_tiles; work += gridDim.x) {
+        const int tile = kWgrad ? work / p.k_splits : work;
         const int m0 = (tile / p.n_tiles) * BM;
         const int n0 = (tile % p.n_tiles) * BN;
+        if (kWgrad) {
+          const int kb0 = (work % p.k_splits) * p.kb_per_split;
+          const int kb1 = min(kb0 + p.kb_per_split, p.kblocks[0]);
+          for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * C::kStageBytes;
+            mbar_expect_tx(&full_bar[stage], C::kStageBytes);
+            // [64 tokens][64 columns] boxes: rows = K, 128 bytes of M (or N) per row
+#pragma unroll
+            for (int hh = 0; hh < BM / 64; ++hh)
+              tma_load_2d(sa + hh * 8192, &p.tma_a[0], &full_bar[stage], m0 + 64 * hh, kb * BK);
+#pragma unroll
+            for (int hh = 0; hh < BN / 64; ++hh)
+              tma_load_2d(sa + kStageBytesA + hh * 8192, &p.tma_b[0], &full_bar[stage], n0 + 64 * hh, kb * BK);
+            if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+          }
+          continue;
+        }
         for (int s = 0; s < p.nseg; ++s) {
           for (int kb = 0; kb < p.kblocks[s]; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -161,25 +186,42 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
   } else if (warp == 1) {
     // -------------------------------------------------------------- MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc<BN>();
+      // MN-major operands (EPI_WGRAD): bits 15/16 of the instruction descriptor
+      constexpr uint32_t idesc = umma_idesc<BN>() | (kWgrad ? (3u << 15) : 0u);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int work = blockIdx.x; work < total_tiles; work += gridDim.x) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
-        for (int kb = 0; kb < total_kblocks; ++kb) {
+        int n_kb = total_kblocks;
+        if (kWgrad) {
+          const int kb0 = (work % p.k_splits) * p.kb_per_split;
+          n_kb = min(kb0 + p.kb_per_split, p.kblocks[0]) - kb0;
+        }
+        for (int kb = 0; kb < n_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
-          const uint64_t da = umma_desc_sw128(sa);
-          const uint64_t db = umma_desc_sw128(sa + kStageBytesA);
+          if (kWgrad) {
+            // MN-major SWIZZLE_128B: 64-element atoms along M/N are 8 KB apart (LBO), 8-row K groups
+            // 1 KB apart (SBO); one K=16 step = 16 rows = 2 KB
+            const uint64_t lbo = static_cast<uint64_t>((8192 >> 4) - 1) << 16;  // umma_desc sets 1
+            const uint64_t da = umma_desc_sw128(sa) + lbo;
+            const uint64_t db = umma_desc_sw128(sa + kStageBytesA) + lbo;
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in 16 B units
-            umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              umma_bf16(d_tmem, da + 128 * k, db + 128 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          } else {
+            const uint64_t da = umma_desc_sw128(sa);
+            const uint64_t db = umma_desc_sw128(sa + kStageBytesA);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in 16 B units
+              umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
           }
           umma_commit(&empty_bar[stage]);
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
@@ -201,7 +243,8 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t chunk_ctr = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int work = blockIdx.x; work < total_tiles; work += gridDim.x) {
+      const int tile = kWgrad ? work / p.k_splits : work;
       const int m0 = (tile / p.n_tiles) * BM;
       const int n0 = (tile % p.n_tiles) * BN;
       mbar_wait(&tmem_full[acc], acc_phase);
@@ -239,7 +282,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = gelu_tanh(v[i]);
         }
-        if (EPI == EPI_F32) {
+        if (epi_is_f32(EPI)) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {  // 8 x 16 B
             float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -260,7 +303,8 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
         fence_proxy_async_smem();
         named_bar_sync(1, kEpiThreads);
         if (ep_tid == 0) {
-          tma_store_2d(&p.tma_out, buf, ncol0, m0);
+          if (kWgrad) tma_reduce_add_2d(&p.tma_out, buf, ncol0, m0);
+          else tma_store_2d(&p.tma_out, buf, ncol0, m0);
           tma_store_commit();
         }
       }
@@ -402,6 +446,8 @@ extern "C" int osudit_gemm_bf16(int nseg, const void* const* a, const int64_t* l
   p.m_tiles = static_cast<int>((M + BM - 1) / BM);
   p.n_tiles = static_cast<int>((N + BN - 1) / BN);
   p.bias = bias;
+  p.k_splits = 1;
+  p.kb_per_split = 0;
   for (int s = 0; s < kMaxSeg; ++s) p.kblocks[s] = 0;
   for (int s = 0; s < nseg; ++s) {
     if (k[s] <= 0 || (k[s] % 8) != 0) return set_error(-1, "gemm: K must be a positive multiple of 8");
@@ -423,4 +469,55 @@ extern "C" int osudit_gemm_bf16(int nseg, const void* const* a, const int64_t* l
   if (epilogue == EPI_F32) return launch<128, EPI_F32>(p, st);
   if (epilogue == EPI_BF16) return launch<128, EPI_BF16>(p, st);
   return launch<128, EPI_BF16_GELU>(p, st);
+}
+
+// out[M,N] (fp32) += dY[rows,M]^T . X[rows,N]: the weight gradient of y = x W^T (W is [M,N] = [out,in]),
+// read straight from the token-major activations (no transposes), K = rows split across CTAs.
+extern "C" int osudit_gemm_wgrad(const void* dy, int64_t ld_dy, const void* x, int64_t ld_x, int64_t rows,
+                                 int64_t M, int64_t N, float* out, int64_t ldo, void* stream) {
+  if (rows <= 0 || M <= 0 || N <= 0 || (M % 8) || (N % 8)) return set_error(-1, "gemm_wgrad: bad shape");
+  const int BN = (N % 256 == 0) ? 256 : 128;
+  GemmParams p;
+  p.nseg = 1;
+  p.M = static_cast<int>(M);
+  p.N = static_cast<int>(N);
+  p.m_tiles = static_cast<int>((M + BM - 1) / BM);
+  p.n_tiles = static_cast<int>((N + BN - 1) / BN);
+  p.bias = nullptr;
+  for (int s = 0; s < kMaxSeg; ++s) p.kblocks[s] = 0;
+  p.kblocks[0] = static_cast<int>((rows + BK - 1) / BK);
+  const int tiles = p.m_tiles * p.n_tiles;
+  int splits = (2 * num_sms() + tiles - 1) / tiles;
+  if (splits > p.kblocks[0]) splits = p.kblocks[0];
+  if (splits < 1) splits = 1;
+  p.kb_per_split = (p.kblocks[0] + splits - 1) / splits;
+  p.k_splits = (p.kblocks[0] + p.kb_per_split - 1) / p.kb_per_split;
+  int rc = make_tensor_map(&p.tma_a[0], dy, M, rows, ld_dy * 2, 64, 64, false);
+  if (rc) return rc;
+  rc = make_tensor_map(&p.tma_b[0], x, N, rows, ld_x * 2, 64, 64, false);
+  if (rc) return rc;
+  rc = make_tensor_map(&p.tma_out, out, N, M, ldo * 4, 32, BM, true);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  using C256 = Cfg<256>;
+  using C128 = Cfg<128>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<256, EPI_WGRAD>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, C256::kSmemBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(gemm_tcgen05_kernel<128, EPI_WGRAD>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, C128::kSmemBytes);
+    if (e != cudaSuccess) return set_error(-5, cudaGetErrorString(e));
+    configured = true;
+  }
+  const int work = tiles * p.k_splits;
+  const int grid = work < num_sms() ? work : num_sms();
+  if (BN == 256)
+    gemm_tcgen05_kernel<256, EPI_WGRAD><<<grid, 64 + epi_threads(EPI_WGRAD), C256::kSmemBytes, st>>>(p);
+  else
+    gemm_tcgen05_kernel<128, EPI_WGRAD><<<grid, 64 + epi_threads(EPI_WGRAD), C128::kSmemBytes, st>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(-6, cudaGetErrorString(e));
+  return 0;
 }

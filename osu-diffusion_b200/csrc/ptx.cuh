@@ -82,6 +82,13 @@ __device__ __forceinline__ void tma_store_2d(const void* tmap, const void* smem_
                ::"l"(tmap), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
                : "memory");
 }
+// smem tile is ADDED (element type from the tensor map, here fp32) into global memory: split-K partials
+__device__ __forceinline__ void tma_reduce_add_2d(const void* tmap, const void* smem_src, int32_t c0,
+                                                  int32_t c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(tmap), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() {
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }

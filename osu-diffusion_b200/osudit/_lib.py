@@ -23,6 +23,7 @@ SIGNATURES = {
     "osudit_last_error": [],
     "osudit_gemm_bf16": [_I, _P, _P, _P, _P, _P, _L, _L, _P, _I, _P, _L, _P],
     "osudit_attn_band": [_P, _P, _I, _I, _I, _I, _I, _I, _P, _I, _P, _P],
+    "osudit_gemm_wgrad": [_P, _L, _P, _L, _L, _L, _L, _P, _L, _P],
     "osudit_attn_band_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "osudit_transpose_bf16": [_P, _P, _L, _L, _L, _I, _P],
     "osudit_gelu": [_P, _P, _P, _L, _I, _P],

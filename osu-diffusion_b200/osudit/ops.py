@@ -201,6 +201,20 @@ def transpose(a: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def gemm_wgrad(dy, x, out):
+    """out[M,N] (fp32) += dy[rows,M]^T @ x[rows,N] (bf16, token-major; no transposes)."""
+    rows, M = dy.shape
+    N = x.shape[1]
+    if x.shape[0] != rows or tuple(out.shape) != (M, N):
+        raise _lib.OsuditError(f"gemm_wgrad: shape mismatch {tuple(dy.shape)} {tuple(x.shape)} -> {tuple(out.shape)}")
+    lib = _lib.load()
+    _lib.check(lib.osudit_gemm_wgrad(_chk(dy, torch.bfloat16, "wgrad.dy"), dy.stride(0),
+                                     _chk(x, torch.bfloat16, "wgrad.x"), x.stride(0), rows, M, N,
+                                     _chk(out, torch.float32, "wgrad.out"), out.stride(0), _stream()),
+               "osudit_gemm_wgrad")
+    return out
+
+
 def gelu(pre, out, dy=None):
     lib = _lib.load()
     _lib.check(lib.osudit_gelu(_chk(pre, torch.bfloat16, "gelu.pre"),

@@ -34,6 +34,11 @@ class TrainWeights:
         self.sig = None
 
     def refresh(self, model):
+        pfp = model.xoc_embedder.playfield_size  # frozen: read it back (a host sync) only when it changes
+        pf_sig = (pfp.data_ptr(), pfp._version)
+        if pf_sig != getattr(self, "pf_sig", None):
+            self.pf = [float(v) for v in pfp.detach().cpu()]
+            self.pf_sig = pf_sig
         sig = tuple((p.data_ptr(), p._version) for p in model.parameters())
         if sig == self.sig:
             return self
@@ -83,8 +88,7 @@ def forward_train(model, tw: TrainWeights, x, t, o, c, y, attn_mask):
 
     kin = 3 * FREQ_SEQ + E
     a_hi, a_lo = _e(rows, kin, device=dev), _e(rows, kin, device=dev)
-    pf = [float(v) for v in model.xoc_embedder.playfield_size.detach().cpu()]
-    ops.embed_xoc(x, o, c, eng.freqs(FREQ_SEQ // 2, dev), pf[0], pf[1], B, a_hi, a_lo)
+    ops.embed_xoc(x, o, c, eng.freqs(FREQ_SEQ // 2, dev), tw.pf[0], tw.pf[1], B, a_hi, a_lo)
     xa = _e(rows, D, dtype=torch.float32, device=dev)
     _gemm3(a_hi, a_lo, tw.first_w, f32(model.xoc_embedder.mlp[0].bias), xa)
     S["a_hi"] = a_hi
@@ -142,9 +146,16 @@ def forward_train(model, tw: TrainWeights, x, t, o, c, y, attn_mask):
     return out, S
 
 
-def _wgrad(dy_t, x_t, out_shape, dev):
-    """dW[N, K] = dY^T[N, rows] . X^T[K, rows]^T with both operands already transposed."""
-    return ops.gemm([dy_t], [x_t], None, ops.EPI_F32, torch.empty(out_shape, dtype=torch.float32, device=dev))
+def _wgrad(dy, x, dev):
+    """dW[out, in] = dY[rows, out]^T . X[rows, in], read token-major (no transposes), fp32."""
+    return ops.gemm_wgrad(dy, x, torch.zeros(dy.shape[1], x.shape[1], dtype=torch.float32, device=dev))
+
+
+def _wgrad_small(dy_f32, x_bf16, dev):
+    """Same for the per-sample (conditioning) matrices whose row count is the batch size: the fp32
+    gradient is rounded to bf16 first."""
+    dy_bf, _ = ops.split_bf16(dy_f32, need_lo=False)
+    return _wgrad(dy_bf, x_bf16, dev)
 
 
 def backward_train(model, tw: TrainWeights, S, dout):
@@ -170,36 +181,34 @@ def backward_train(model, tw: TrainWeights, S, dout):
         hidden = sv["pre"].shape[1]
         # ---- MLP branch: x_out = xb + gate_mlp * y2
         dy2 = ops.gate_residual_bwd(dx, sv["y2"], mod, dmod, base + 5 * D, B, T, _e(rows, D, device=dev))
-        dy2_t = ops.transpose(dy2)
-        grads[blk.mlp.fc2.weight] = _wgrad(dy2_t, ops.transpose(sv["u"]), (D, hidden), dev)
+        grads[blk.mlp.fc2.weight] = _wgrad(dy2, sv["u"], dev)
         grads[blk.mlp.fc2.bias] = ops.colsum(dy2, z32(D))
         du = ops.gemm([dy2], [bw["fc2_wt"]], None, ops.EPI_BF16, _e(rows, hidden, device=dev))
         dpre = ops.gelu(sv["pre"], du, dy=du)  # in place over du
-        grads[blk.mlp.fc1.weight] = _wgrad(ops.transpose(dpre), ops.transpose(sv["h2"]), (hidden, D), dev)
+        grads[blk.mlp.fc1.weight] = _wgrad(dpre, sv["h2"], dev)
         grads[blk.mlp.fc1.bias] = ops.colsum(dpre, z32(hidden))
         dh2 = ops.gemm([dpre], [bw["fc1_wt"]], None, ops.EPI_BF16, _e(rows, D, device=dev))
         ops.ln_modulate_bwd(sv["xb"], dh2, mod, dmod, base + 3 * D, base + 4 * D, B, T, dx, True)
         # ---- attention branch: xb = xa + gate_msa * y1
         dy1 = ops.gate_residual_bwd(dx, sv["y1"], mod, dmod, base + 2 * D, B, T, dy2)  # reuse buffer
-        grads[blk.attn.out_proj.weight] = _wgrad(ops.transpose(dy1), ops.transpose(sv["att"]), (D, D), dev)
+        grads[blk.attn.out_proj.weight] = _wgrad(dy1, sv["att"], dev)
         grads[blk.attn.out_proj.bias] = ops.colsum(dy1, z32(D))
         datt = ops.gemm([dy1], [bw["out_wt"]], None, ops.EPI_BF16, dh2)  # reuse buffer
         dqkv = ops.attn_band_bwd(sv["qkv"], sv["att"], datt, sv["lse"], _e(rows, 3 * D, device=dev), B, T, H,
                                  D // H, spec.w_left, spec.w_right)
-        grads[blk.attn.in_proj_weight] = _wgrad(ops.transpose(dqkv), ops.transpose(sv["h1"]), (3 * D, D), dev)
+        grads[blk.attn.in_proj_weight] = _wgrad(dqkv, sv["h1"], dev)
         grads[blk.attn.in_proj_bias] = ops.colsum(dqkv, z32(3 * D))
         dh1 = ops.gemm([dqkv], [bw["qkv_wt"]], None, ops.EPI_BF16, datt)  # reuse buffer
         ops.ln_modulate_bwd(sv["xa"], dh1, mod, dmod, base, base + D, B, T, dx, True)
 
     # ---- first layer: x0 = a W^T + b  (no gradient to the inputs)
     first = model.xoc_embedder.mlp[0]
-    grads[first.weight] = _wgrad(ops.transpose(dx), ops.transpose(S["a_hi"]), tuple(first.weight.shape), dev)
+    grads[first.weight] = _wgrad_small(dx, S["a_hi"], dev)
     grads[first.bias] = ops.colsum(dx, z32(D))
 
     # ---- conditioning path: mod = s Wmod^T + bmod, s = SiLU(temb + table[y])
     dmod_bf, _ = ops.split_bf16(dmod, need_lo=False)
-    dmod_t = ops.transpose(dmod)
-    gw = _wgrad(dmod_t, ops.transpose(S["c_hi"]), (mod.shape[1], D), dev)
+    gw = _wgrad(dmod_bf, S["c_hi"], dev)
     gb = ops.colsum(dmod, z32(mod.shape[1]))
     mods = [b.adaLN_modulation[1] for b in model.blocks] + [fl.adaLN_modulation[1]]
     r0 = 0
@@ -213,13 +222,12 @@ def backward_train(model, tw: TrainWeights, S, dout):
     dcond = ops.silu_bwd(S["temb"], ds, torch.empty_like(ds), table=S["table"], y=S["y"], dtable=grads[table_p])
     # t-MLP: temb = SiLU(tf W0^T + b0) W2^T + b2
     t0, t2 = model.t_embedder.mlp[0], model.t_embedder.mlp[2]
-    dcond_t = ops.transpose(dcond)
-    grads[t2.weight] = _wgrad(dcond_t, ops.transpose(S["s1_hi"]), (D, D), dev)
-    grads[t2.bias] = ops.colsum(dcond, z32(D))
     dcond_bf, _ = ops.split_bf16(dcond, need_lo=False)
+    grads[t2.weight] = _wgrad(dcond_bf, S["s1_hi"], dev)
+    grads[t2.bias] = ops.colsum(dcond, z32(D))
     ds1 = ops.gemm([dcond_bf], [tw.t2_wt], None, ops.EPI_F32, torch.empty_like(ds))
     dh1t = ops.silu_bwd(S["h1t"], ds1, torch.empty_like(ds1))
-    grads[t0.weight] = _wgrad(ops.transpose(dh1t), ops.transpose(S["tf_hi"]), (D, FREQ_T), dev)
+    grads[t0.weight] = _wgrad_small(dh1t, S["tf_hi"], dev)
     grads[t0.bias] = ops.colsum(dh1t, z32(D))
     return [grads.get(p) if p.requires_grad else None for p in model.parameters()]
 
