@@ -26,7 +26,6 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
-#include <stdlib.h>
 
 #include "common.h"
 #include "ptx.cuh"
@@ -42,13 +41,13 @@ constexpr int kQ = 128;        // queries per tile
 constexpr int kWin = 384;      // keys per window
 constexpr int kHD = 64;
 constexpr int kTile = kQ * kHD * 2;            // 16 KB: one [128][64] bf16 box
-constexpr int kSmemQ = 0;                      // 2 boxes (double-buffered across tiles)
-constexpr int kSmemK = kSmemQ + 2 * kTile;     // 3 boxes
+constexpr int kSmemQ = 0;
+constexpr int kSmemK = kSmemQ + kTile;         // 3 boxes
 constexpr int kSmemV = kSmemK + 3 * kTile;     // 3 boxes
 constexpr int kSmemP = kSmemV + 3 * kTile;     // 6 boxes: P[128][384] as 6 K-blocks of 64 keys
 constexpr int kSmemBar = kSmemP + 6 * kTile;
 constexpr int kSmemX = kSmemBar + 256;         // (reference, sum) exchange between the two column halves
-constexpr int kSmemBytes = kSmemX + 2 * 128 * 8;  // 231680 B of the 232448 B a CTA may use
+constexpr int kSmemBytes = kSmemX + 2 * 128 * 8 + 1024;
 constexpr int kSoftmaxThreads = 256;          // 8 warps: two per TMEM lane quadrant, 192 columns each
 constexpr int kThreads = 64 + kSoftmaxThreads;
 constexpr uint32_t kColS = 0, kColO = kWin;    // TMEM columns: S 0-383, O0 384-447, O1 448-511
@@ -109,20 +108,20 @@ __device__ __forceinline__ TileInfo decode_tile(const Params& p, int tile) {
 // far inside bf16/fp32 range, and the final O / sum is independent of the reference.
 constexpr float kJump = 24.0f;
 
-// kAblate (debug only, tools/attn_debug.py): 0 = real kernel; 1 = softmax warps skip TMEM loads and
-// math (zeros into P); 2 = TMEM loads but no math; 3 = math but no P stores to shared memory.
-template <int kAblate>
 __global__ void __launch_bounds__(kThreads, 1) attn_window_kernel(const __grid_constant__ Params p) {
-  extern __shared__ __align__(1024) uint8_t smem[];  // SWIZZLE_128B boxes need 1024-byte alignment
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemBar);
-  uint64_t* k_full = bars + 13;   // [3] TMA: K slab j landed ([1] also covers Q)
+  uint64_t* qk_full = bars + 0;   // TMA: Q + 3 K landed
   uint64_t* v_full = bars + 1;    // TMA: 3 V landed
-  uint64_t* s_done = bars + 2;    // [3] MMA: slab j of S complete (K slab j smem reusable)
-  uint64_t* o_done = bars + 5;    // [2] MMA: O_h complete (P_h smem reusable; after [1]: V reusable)
-  uint64_t* o_free = bars + 7;    // epilogue: O0 and O1 fully read (128 arrivals, half 1)
-  uint64_t* s_free = bars + 8;    // [3] 128-column slab j of S fully read
-  uint64_t* p_full = bars + 11;   // [2] P_h written (128 arrivals: the owning half)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* s01_done = bars + 2;  // MMA: slabs 0,1 of S complete (what half 0 reads)
+  uint64_t* s_done = bars + 3;    // MMA: all of S complete (half 1 may start; Q/K smem reusable)
+  uint64_t* o_done = bars + 4;    // [2] MMA: O_h complete (P_h smem reusable; after [1]: V reusable)
+  uint64_t* o_free = bars + 6;    // epilogue: O0 and O1 fully read (128 arrivals, half 1)
+  uint64_t* s_free = bars + 7;    // [3] 128-column slab j of S fully read
+  uint64_t* p_full = bars + 10;   // [2] P_h written (128 arrivals: the owning half)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
   float2* xchg = reinterpret_cast<float2*>(smem + kSmemX);  // [2 parities][128 rows] half 0's (ref, sum)
 
   const int warp = threadIdx.x >> 5;
@@ -130,17 +129,18 @@ __global__ void __launch_bounds__(kThreads, 1) attn_window_kernel(const __grid_c
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tma_qkv);
-    for (int j = 0; j < 3; ++j) mbar_init(&k_full[j], 1);
+    mbar_init(qk_full, 1);
     mbar_init(v_full, 1);
-    for (int j = 0; j < 3; ++j) mbar_init(&s_done[j], 1);
+    mbar_init(s01_done, 1);
+    mbar_init(s_done, 1);
     mbar_init(&o_done[0], 1);
     mbar_init(&o_done[1], 1);
-    mbar_init(o_free, 4);         // per-warp arrivals (see warp_mbar_arrive)
-    mbar_init(&s_free[0], 4);    // columns   0-127: the 4 warps of half 0
-    mbar_init(&s_free[1], 8);    // columns 128-255: both halves
-    mbar_init(&s_free[2], 4);    // columns 256-383: half 1
-    mbar_init(&p_full[0], 4);
-    mbar_init(&p_full[1], 4);
+    mbar_init(o_free, 128);
+    mbar_init(&s_free[0], 128);  // columns   0-127: half 0 only
+    mbar_init(&s_free[1], 256);  // columns 128-255: both halves
+    mbar_init(&s_free[2], 128);  // columns 256-383: half 1 only
+    mbar_init(&p_full[0], 128);
+    mbar_init(&p_full[1], 128);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -160,23 +160,14 @@ __global__ void __launch_bounds__(kThreads, 1) attn_window_kernel(const __grid_c
       for (int i = 0; i < n_my; ++i) {
         const TileInfo t = decode_tile(p, blockIdx.x + i * gridDim.x);
         const uint32_t prev = (i & 1) ^ 1;  // parity of tile i-1's completion (passes at i == 0)
-        // K slabs in the order S consumes them (1, 0, 2); each K box is free as soon as the same
-        // slab of S(i-1) is complete.  Q is double-buffered: its box was last read by S(i-2),
-        // whose completion this thread already observed while loading tile i-1.
-        const int order[3] = {1, 0, 2};
+        mbar_wait(s_done, prev);            // S(i-1) done: Q/K smem free
+        mbar_expect_tx(qk_full, 4 * kTile);
+        tma_load_3d(smem + kSmemQ, &p.tma_qkv, qk_full, t.h * kHD, t.q0, t.b);
 #pragma unroll
-        for (int jj = 0; jj < 3; ++jj) {
-          const int j = order[jj];
-          mbar_wait(&s_done[j], prev);
-          if (kAblate == 7) { mbar_arrive(&k_full[j]); continue; }
-          mbar_expect_tx(&k_full[j], (jj == 0 ? 2 : 1) * kTile);
-          if (jj == 0)
-            tma_load_3d(smem + kSmemQ + (i & 1) * kTile, &p.tma_qkv, &k_full[j], t.h * kHD, t.q0, t.b);
-          tma_load_3d(smem + kSmemK + j * kTile, &p.tma_qkv, &k_full[j], p.D + t.h * kHD,
+        for (int j = 0; j < 3; ++j)
+          tma_load_3d(smem + kSmemK + j * kTile, &p.tma_qkv, qk_full, p.D + t.h * kHD,
                       t.kw0 + j * kQ, t.b);
-        }
         mbar_wait(&o_done[1], prev);        // PV_1(i-1), the last reader of V(i-1), is done
-        if (kAblate == 7) { mbar_arrive(v_full); continue; }
         mbar_expect_tx(v_full, 3 * kTile);
 #pragma unroll
         for (int j = 0; j < 3; ++j)
@@ -186,11 +177,10 @@ __global__ void __launch_bounds__(kThreads, 1) attn_window_kernel(const __grid_c
     }
   } else if (warp == 1) {
     // -------------------------------------------------------------------- MMA issuer
-    // Both column halves of the softmax start a tile on slab 1 of S (which both release first) and
-    // finish on their private slab (0 resp. 2), so per tile i the tensor pipe is fed in event order:
-    //   S(i+1) slab 1 | S(i+1) slab 0 | PV_0(i) | S(i+1) slab 2 | PV_1(i)
-    // The halves drift half a period apart, so each half's MMA latency hides behind the other
-    // half's exponentials.
+    // The two column halves of the softmax run staggered (half 0 starts as soon as slabs 0,1 of S
+    // exist, half 1 after slab 2), so the tensor pipe interleaves, per tile i:
+    //   S(i+1) slab 0 | PV_0(i) | S(i+1) slab 1 | S(i+1) slab 2 | PV_1(i)
+    // and each half's MMA latency is hidden behind the other half's exponentials.
     if (lane == 0) {
       constexpr uint32_t idesc_s = idesc(128, false);
       constexpr uint32_t idesc_o = idesc(kHD, true);
@@ -198,17 +188,14 @@ __global__ void __launch_bounds__(kThreads, 1) attn_window_kernel(const __grid_c
       const uint32_t sk = smem_u32(smem + kSmemK);
       const uint32_t sv = smem_u32(smem + kSmemV);
       const uint32_t sp = smem_u32(smem + kSmemP);
+      const uint64_t dq = desc_sw128(sq);
       auto issue_s_slab = [&](int i, int j) {  // S(i)[:, 128j : 128j+128] = Q K_j^T
-        mbar_wait(&k_full[j], i & 1);
         mbar_wait(&s_free[j], (i & 1) ^ 1);
         tc_fence_after();
-        const uint64_t dq = desc_sw128(sq + (i & 1) * kTile);
         const uint64_t dk = desc_sw128(sk + j * kTile);
-        if (kAblate != 5 && kAblate != 6) {
 #pragma unroll
-          for (int k = 0; k < kHD / 16; ++k)
-            umma_bf16(tmem_base + kColS + j * 128, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
-        }
+        for (int k = 0; k < kHD / 16; ++k)
+          umma_bf16(tmem_base + kColS + j * 128, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
       };
       auto issue_pv_half = [&](int i, int h) {  // O_h = P[:, 192h : 192h+192] V[192h : 192h+192]
         mbar_wait(&p_full[h], i & 1);
@@ -218,33 +205,35 @@ __global__ void __launch_bounds__(kThreads, 1) attn_window_kernel(const __grid_c
           const int kb = 3 * h + b3;           // 64-key block of P; V box = kb / 2
           const uint64_t dp = desc_sw128(sp + kb * kTile);
           const uint64_t dv = desc_sw128(sv + (kb >> 1) * kTile + (kb & 1) * (64 * 128));
-          if (kAblate != 4 && kAblate != 6) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)        // 16 keys: +32 B along P's row, +16 rows (2048 B) in V
-              umma_bf16(tmem_base + kColO + h * kHD, dp + 2 * k, dv + 128 * k, idesc_o, (b3 | k) != 0);
-          }
+          for (int k = 0; k < 4; ++k)          // 16 keys: +32 B along P's row, +16 rows (2048 B) in V
+            umma_bf16(tmem_base + kColO + h * kHD, dp + 2 * k, dv + 128 * k, idesc_o, (b3 | k) != 0);
         }
         umma_commit(&o_done[h]);
       };
-      auto issue_s = [&](int i, int j) {
-        issue_s_slab(i, j);
-        umma_commit(&s_done[j]);
-      };
       if (n_my > 0) {
-        issue_s(0, 1);
-        issue_s(0, 0);
-        issue_s(0, 2);
+        mbar_wait(qk_full, 0);
+        issue_s_slab(0, 0);
+        issue_s_slab(0, 1);
+        umma_commit(s01_done);
+        issue_s_slab(0, 2);
+        umma_commit(s_done);
       }
       for (int i = 0; i < n_my; ++i) {
         const bool has_next = i + 1 < n_my;
         if (has_next) {
-          issue_s(i + 1, 1);  // both halves finish their slab-1 block first
-          issue_s(i + 1, 0);  // released at the end of half 0
+          mbar_wait(qk_full, (i + 1) & 1);
+          issue_s_slab(i + 1, 0);
         }
         mbar_wait(v_full, i & 1);
         mbar_wait(o_free, (i & 1) ^ 1);
         issue_pv_half(i, 0);
-        if (has_next) issue_s(i + 1, 2);  // released at the end of half 1 (slab 2 last: frees Q/K)
+        if (has_next) {
+          issue_s_slab(i + 1, 1);
+          umma_commit(s01_done);
+          issue_s_slab(i + 1, 2);
+          umma_commit(s_done);
+        }
         issue_pv_half(i, 1);
       }
     }
@@ -261,34 +250,40 @@ __global__ void __launch_bounds__(kThreads, 1) attn_window_kernel(const __grid_c
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     uint8_t* p_row = smem + kSmemP + row * 128;
     const int swz = row & 7;
-    // this thread's three 64-column blocks of the window in processing order: the slab-1 block
-    // first, then the two blocks of the private slab (half 0: 2,0,1; half 1: 3,4,5)
-    auto block_of = [&](int nb) { return half == 0 ? (nb == 0 ? 2 : nb - 1) : 3 + nb; };
+    const int cbeg = half * 6;  // this thread's chunks: [cbeg, cbeg + 6)
 
     for (int i = 0; i < n_my; ++i) {
       const TileInfo t = decode_tile(p, blockIdx.x + i * gridDim.x);
       const uint32_t par = i & 1;
-      // allowed columns of this row; columns allowed for EVERY row of this warp (no masking
-      // needed there); 64-column blocks (= pairs of chunks) holding any allowed column of the warp
-      const int key_lo = -t.kw0, key_hi = p.T - 1 - t.kw0;  // window columns that are real keys
-      const int c_lo = max(max(row + p.lo, key_lo), 0);
-      const int c_hi = min(min(row + p.hi, key_hi), kWin - 1);
-      const int wi_lo = max(max(quad * 32 + 31 + p.lo, key_lo), 0);
-      const int wi_hi = min(min(quad * 32 + p.hi, key_hi), kWin - 1);
-      const int wa_lo = max(max(quad * 32 + p.lo, key_lo), 0);
-      const int wa_hi = min(min(quad * 32 + 31 + p.hi, key_hi), kWin - 1);
+      // allowed columns of this row, and the chunk range any row of this warp needs
+      const int c_lo = max(max(row + p.lo, -t.kw0), 0);
+      const int c_hi = min(min(row + p.hi, p.T - 1 - t.kw0), kWin - 1);
+      const int ch_lo = max(max(quad * 32 + p.lo, -t.kw0), 0) >> 5;
+      const int ch_hi = min(min(quad * 32 + 31 + p.hi, p.T - 1 - t.kw0), kWin - 1) >> 5;
+      auto in_range = [&](int c) { return c >= ch_lo && c <= ch_hi; };
 
       float ref = -INFINITY;  // running reference (integer-valued, log2 domain)
       float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
 
-      // rare: the reference moved up by more than kJump: rescale the blocks this thread already
-      // wrote (none of them has been published to the tensor pipe yet: p_full[half] fires after
-      // the thread's last block)
-      auto rescale_written = [&](int nb_done, float factor) {
-        for (int bb = 0; bb < nb_done; ++bb) {
-          uint8_t* blk = p_row + block_of(bb) * kTile;
-          for (int j = 0; j < 8; ++j) {
-            uint4* ptr = reinterpret_cast<uint4*>(blk + (j << 4));
+      auto store_chunk = [&](int c, const uint32_t(&packed)[16]) {
+        // 32 keys = 64 B = four 16-byte chunks of the 128-byte row in K-block c/2
+        uint8_t* blk = p_row + (c >> 1) * kTile;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int chunk = (c & 1) * 4 + j;
+          *reinterpret_cast<uint4*>(blk + ((chunk ^ swz) << 4)) =
+              make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+        }
+      };
+      // rare: the reference moved up by more than kJump: rescale what this thread already wrote
+      // (nothing of it has been published to the tensor pipe yet: p_full[half] fires after the
+      // thread's last chunk)
+      auto rescale_written = [&](int c_end, float factor) {
+        for (int cc = cbeg; cc < c_end; ++cc) {
+          uint8_t* blk = p_row + (cc >> 1) * kTile;
+          for (int j = 0; j < 4; ++j) {
+            const int chunk = (cc & 1) * 4 + j;
+            uint4* ptr = reinterpret_cast<uint4*>(blk + ((chunk ^ swz) << 4));
             uint4 w = *ptr;
             uint32_t* e = reinterpret_cast<uint32_t*>(&w);
 #pragma unroll
@@ -301,112 +296,74 @@ __global__ void __launch_bounds__(kThreads, 1) attn_window_kernel(const __grid_c
         }
         sum0 *= factor; sum1 *= factor; sum2 *= factor; sum3 *= factor;
       };
+      auto emit = [&](uint32_t(&v)[32], int c) {
+        uint32_t packed[16];
+        if (!in_range(c)) {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) packed[k] = 0u;
+          store_chunk(c, packed);
+          return;
+        }
+        const int base = c * 32;
+        if (!(base >= c_lo && base + 31 <= c_hi)) {  // boundary chunk: masked scores become -inf
+          const int klo = c_lo - base, khi = c_hi - base;
+#pragma unroll
+          for (int k = 0; k < 32; ++k)
+            if (k < klo || k > khi) v[k] = 0xff800000u;
+        }
+        float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < 32; k += 2) {
+          m0 = fmaxf(m0, __uint_as_float(v[k]));
+          m1 = fmaxf(m1, __uint_as_float(v[k + 1]));
+        }
+        const float cm = fmaxf(m0, m1) * p.scale_log2;
+        if (cm > ref + kJump) {  // also taken on the thread's first allowed chunk (ref = -inf)
+          const float new_ref = ceilf(cm);
+          if (ref != -INFINITY) rescale_written(c, fast_exp2(ref - new_ref));
+          ref = new_ref;
+        }
+        const float off = (ref == -INFINITY) ? 0.f : ref;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {  // two groups of 16 columns keep the live register set small
+          float pv[16];
+#pragma unroll
+          for (int k = 0; k < 16; ++k)
+            pv[k] = fast_exp2(fmaf(__uint_as_float(v[16 * g + k]), p.scale_log2, -off));
+#pragma unroll
+          for (int k = 0; k < 16; k += 4) {
+            sum0 += pv[k];
+            sum1 += pv[k + 1];
+            sum2 += pv[k + 2];
+            sum3 += pv[k + 3];
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) packed[8 * g + k] = pack_bf16(pv[2 * k], pv[2 * k + 1]);
+        }
+        store_chunk(c, packed);
+      };
 
-      warp_mbar_wait(&s_done[1], par);  // slab 1 of S exists
+      // S slabs this half reads exist; PV_half(i-1) has finished reading this half's P blocks
+      mbar_wait(half == 0 ? s01_done : s_done, par);
+      if (i > 0) mbar_wait(&o_done[half], par ^ 1);
       tc_fence_after();
 
       uint32_t ra[32], rb[32];
-      {
-        const int base = block_of(0) * 64;
-        if (base + 63 >= wa_lo && base <= wa_hi) {
-          if (kAblate != 1) {
-            tmem_ld_32x32(t_lane + kColS + base, ra);
-            tmem_ld_32x32(t_lane + kColS + base + 32, rb);
-          }
-        }
-      }
-#pragma unroll 1  // one 64-column block per iteration; the body must stay in the instruction cache
-      for (int nb = 0; nb < 3; ++nb) {
-        const int blk_idx = block_of(nb);
-        const int base = blk_idx * 64;
-        uint8_t* blk = p_row + blk_idx * kTile;
-        const bool active = (kAblate == 0 || kAblate >= 3) && base + 63 >= wa_lo && base <= wa_hi;  // warp-uniform
-        if (!active) {
-          if (nb == 0 && i > 0) warp_mbar_wait(&o_done[half], par ^ 1);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(blk + (j << 4)) = make_uint4(0, 0, 0, 0);
-        } else {
-          tmem_ld_wait();
-          if (!(base >= wi_lo && base + 63 <= wi_hi)) {  // warp-uniform: some row needs masking
-            const int klo = c_lo - base, khi = c_hi - base;
-#pragma unroll
-            for (int k = 0; k < 32; ++k) {
-              if (k < klo || k > khi) ra[k] = 0xff800000u;  // -inf
-              if (k + 32 < klo || k + 32 > khi) rb[k] = 0xff800000u;
-            }
-          }
-          float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-#pragma unroll
-          for (int k = 0; k < 32; k += 2) {
-            m0 = fmaxf(m0, __uint_as_float(ra[k]));
-            m1 = fmaxf(m1, __uint_as_float(ra[k + 1]));
-            m2 = fmaxf(m2, __uint_as_float(rb[k]));
-            m3 = fmaxf(m3, __uint_as_float(rb[k + 1]));
-          }
-          const float cm = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * p.scale_log2;
-          if (cm > ref + kJump) {  // also taken on the thread's first allowed block (ref = -inf)
-            const float new_ref = ceilf(cm);
-            if (ref != -INFINITY) rescale_written(nb, fast_exp2(ref - new_ref));
-            ref = new_ref;
-          }
-          const float off = (ref == -INFINITY) ? 0.f : ref;
-          uint32_t packed[32];
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {  // groups of 16 columns keep the live register set small
-            float pv[16];
-#pragma unroll
-            for (int k = 0; k < 16; ++k) {
-              const uint32_t raw = g < 2 ? ra[16 * g + k] : rb[16 * (g - 2) + k];
-              pv[k] = fast_exp2(fmaf(__uint_as_float(raw), p.scale_log2, -off));
-            }
-#pragma unroll
-            for (int k = 0; k < 16; k += 4) {
-              sum0 += pv[k];
-              sum1 += pv[k + 1];
-              sum2 += pv[k + 2];
-              sum3 += pv[k + 3];
-            }
-#pragma unroll
-            for (int k = 0; k < 8; ++k) packed[8 * g + k] = pack_bf16(pv[2 * k], pv[2 * k + 1]);
-          }
-          // the raw scores are consumed: start fetching the next block while this one is stored
-          if (nb == 0) {  // the remaining two blocks live in this half's private slab
-            warp_mbar_wait(&s_done[half == 0 ? 0 : 2], par);
-            tc_fence_after();
-          }
-          if (nb + 1 < 3) {
-            const int nbase = block_of(nb + 1) * 64;
-            if (nbase + 63 >= wa_lo && nbase <= wa_hi) {
-              tmem_ld_32x32(t_lane + kColS + nbase, ra);
-              tmem_ld_32x32(t_lane + kColS + nbase + 32, rb);
-            }
-          }
-          // PV_half(i-1) must have finished reading this half's P blocks before the first store;
-          // waiting here (not at the top of the tile) hides its latency behind the first block
-          if (nb == 0 && i > 0) warp_mbar_wait(&o_done[half], par ^ 1);
-#pragma unroll
-          for (int j = 0; j < 8; ++j)  // 64 keys = the whole 128-byte row of this K-block
-            if (kAblate != 3 || packed[4 * j] == 0x12345678u)
-              *reinterpret_cast<uint4*>(blk + ((j ^ swz) << 4)) =
-                  make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-        }
-        if (!active) {
-          if (kAblate == 2) tmem_ld_wait();
-          if (nb == 0) {
-            warp_mbar_wait(&s_done[half == 0 ? 0 : 2], par);
-            tc_fence_after();
-          }
-          if (nb + 1 < 3) {
-            const int nbase = block_of(nb + 1) * 64;
-            if (kAblate != 1 && nbase + 63 >= wa_lo && nbase <= wa_hi) {
-              tmem_ld_32x32(t_lane + kColS + nbase, ra);
-              tmem_ld_32x32(t_lane + kColS + nbase + 32, rb);
-            }
-          }
-        }
-        if (nb == 0 || nb == 2) {  // slab 1 after the first block, the private slab after the last
+      if (in_range(cbeg)) tmem_ld_32x32(t_lane + kColS + cbeg * 32, ra);
+#pragma unroll 1  // keep the body (2 x emit) resident in the instruction cache
+      for (int u = 0; u < 6; u += 2) {
+        const int c = cbeg + u;
+        tmem_ld_wait();
+        if (in_range(c + 1)) tmem_ld_32x32(t_lane + kColS + (c + 1) * 32, rb);
+        emit(ra, c);
+        tmem_ld_wait();
+        if (u + 2 < 6 && in_range(c + 2)) tmem_ld_32x32(t_lane + kColS + (c + 2) * 32, ra);
+        emit(rb, c + 1);
+        // release slabs of S: half 0 owns chunks 0-5 (slab 0, first half of slab 1), half 1 6-11
+        if ((half == 0 && u == 2) || (half == 1 && u == 0) || u == 4) {
+          const int slab = (half == 0) ? (u == 2 ? 0 : 1) : (u == 0 ? 1 : 2);
           tc_fence_before();
-          warp_mbar_arrive(&s_free[nb == 0 ? 1 : (half == 0 ? 0 : 2)]);
+          mbar_arrive(&s_free[slab]);
         }
       }
       const float sum = (sum0 + sum1) + (sum2 + sum3);
@@ -414,20 +371,20 @@ __global__ void __launch_bounds__(kThreads, 1) attn_window_kernel(const __grid_c
       if (half == 0) {
         xc[row] = make_float2(ref, sum);
         fence_proxy_async_smem();
-        warp_mbar_arrive(&p_full[0]);
+        mbar_arrive(&p_full[0]);
         // publishes xc to half 1 (which bar.syncs); ids alternate per tile because half 0 may
         // already be one tile ahead of half 1 (never two: s_free[1] ties them together)
         asm volatile("bar.arrive %0, 256;" ::"r"(1 + static_cast<int>(par)) : "memory");
         continue;
       }
       fence_proxy_async_smem();
-      warp_mbar_arrive(&p_full[1]);
+      mbar_arrive(&p_full[1]);
       named_bar_sync(1 + par, kSoftmaxThreads);
       const float2 other = xc[row];
 
       // ---- epilogue (half 1): (w0 O0 + w1 O1) / (w0 sum0 + w1 sum1) -> bf16 -> global
-      warp_mbar_wait(&o_done[0], par);
-      warp_mbar_wait(&o_done[1], par);
+      mbar_wait(&o_done[0], par);
+      mbar_wait(&o_done[1], par);
       tc_fence_after();
       const float rmax = fmaxf(other.x, ref);
       const float w_a = (other.x == -INFINITY) ? 0.f : fast_exp2(other.x - rmax);
@@ -444,7 +401,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_window_kernel(const __grid_c
         tmem_ld_wait();
         if (hh == 1) {
           tc_fence_before();
-          warp_mbar_arrive(o_free);
+          mbar_arrive(o_free);
         }
         if (q < p.T) {
           auto mix = [&](int k) {
@@ -493,37 +450,14 @@ int attn_window_launch(const void* qkv, void* out, int B, int T, int H, int w_le
   p.hi = kQ + w_right;
   p.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(kHD));
   static bool configured = false;
-#ifdef OSUDIT_ATTN_ABLATIONS  // bottleneck analysis builds only (tools/attn_ablate.py)
-  static int ablate = 0;
   if (!configured) {
-    const char* env = getenv("OSUDIT_ATTN_ABLATE");
-    ablate = env ? atoi(env) : 0;
-    for (auto kern : {attn_window_kernel<0>, attn_window_kernel<1>, attn_window_kernel<2>, attn_window_kernel<3>,
-                      attn_window_kernel<4>, attn_window_kernel<5>, attn_window_kernel<6>, attn_window_kernel<7>}) {
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-      if (e != cudaSuccess) return set_error(-5, cudaGetErrorString(e));
-    }
-    configured = true;
-  }
-  const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  if (ablate == 1) attn_window_kernel<1><<<grid, kThreads, kSmemBytes, stream>>>(p);
-  else if (ablate == 2) attn_window_kernel<2><<<grid, kThreads, kSmemBytes, stream>>>(p);
-  else if (ablate == 3) attn_window_kernel<3><<<grid, kThreads, kSmemBytes, stream>>>(p);
-  else if (ablate == 4) attn_window_kernel<4><<<grid, kThreads, kSmemBytes, stream>>>(p);
-  else if (ablate == 5) attn_window_kernel<5><<<grid, kThreads, kSmemBytes, stream>>>(p);
-  else if (ablate == 6) attn_window_kernel<6><<<grid, kThreads, kSmemBytes, stream>>>(p);
-  else if (ablate == 7) attn_window_kernel<7><<<grid, kThreads, kSmemBytes, stream>>>(p);
-  else attn_window_kernel<0><<<grid, kThreads, kSmemBytes, stream>>>(p);
-#else
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_window_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(attn_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          kSmemBytes);
     if (e != cudaSuccess) return set_error(-5, cudaGetErrorString(e));
     configured = true;
   }
   const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  attn_window_kernel<0><<<grid, kThreads, kSmemBytes, stream>>>(p);
-#endif
+  attn_window_kernel<<<grid, kThreads, kSmemBytes, stream>>>(p);
   OSUDIT_CHECK_LAUNCH();
   return 0;
 }

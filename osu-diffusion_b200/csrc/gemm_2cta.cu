@@ -1,0 +1,311 @@
+// 2-CTA (cta_group::2) variant of the bf16 GEMM for the four large per-block contractions
+// (models.py:164-170 QKV / out-proj, models.py:112-119 fc1+GELU / fc2).
+//
+// A CTA pair (one TPC) computes a 256 x 256 output tile with UMMA M=256, N=256: each CTA stages its
+// own 128 rows of A and its own 128 rows (N half) of B, so per MMA every SM reads 8 KB of shared
+// memory instead of 12 KB and TMA writes 32 KB instead of 48 KB per k-block — the 1-CTA kernel's
+// K=768 shapes sit at ~70 % tensor-pipe activity because of exactly that traffic (profiles/r01).
+//
+//   both CTAs   warp 0: TMA producer (cp.async.bulk.tensor ... .cta_group::2: completion bytes land on
+//               the LEADER's full barrier); warps 2-9: epilogue of the CTA's own 128 accumulator rows
+//   leader CTA  warp 1 lane 0: tcgen05.mma.cta_group::2 issuer; tcgen05.commit multicasts to the empty /
+//               tmem_full barriers of both CTAs
+//   peer CTA    epilogue warps arrive remotely (mapa) on the leader's tmem_empty barrier
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace osudit {
+
+int make_tensor_map_2d(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t stride_bytes,
+                       uint32_t b0, uint32_t b1, bool is_f32);
+
+namespace g2 {
+
+constexpr int BM = 128;        // rows per CTA (256 per pair)
+constexpr int BN = 256;        // columns per pair; each CTA stages BN/2 rows of B
+constexpr int BK = 64;
+constexpr int kStages = 6;
+constexpr int kBytesA = BM * BK * 2;
+constexpr int kBytesB = (BN / 2) * BK * 2;
+constexpr int kStageBytes = kBytesA + kBytesB;  // 32 KB per CTA
+constexpr int kStagingBytes = BM * 128;
+constexpr int kThreads = 64 + 256;
+constexpr int kSmemBytes = kStages * kStageBytes + 2 * kStagingBytes + 1024;
+
+struct Params {
+  CUtensorMap tma_a, tma_b, tma_out;
+  int kblocks, M, N, m_tiles, n_tiles;
+  const float* bias;
+};
+
+enum : int { EPI_BF16 = 1, EPI_BF16_GELU = 2 };
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_rank0(uint32_t smem_addr) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(smem_addr));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const void* tmap, uint32_t leader_bar,
+                                                 int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                               uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {  // arrives on `bar` in BOTH CTAs
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"(static_cast<uint16_t>(3))
+      : "memory");
+}
+__device__ __forceinline__ uint64_t desc_sw128(uint32_t smem_addr) {
+  return static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF) | (1ull << 16) |
+         (static_cast<uint64_t>(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ float gelu_tanh(float x) {
+  // 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3))) with the hardware tanh (one MUFU op per element;
+  // its 2^-11 error is far below the bf16 rounding of the result that follows)
+  const float u = x * fmaf(x * x, 0.044715f * 0.7978845608028654f, 0.7978845608028654f);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
+}
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm2_kernel(const __grid_constant__ Params p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* staging = smem + kStages * kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + 2 * kStagingBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full = empty_bar + kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const int total_tiles = p.m_tiles * p.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tma_a);
+    tma_prefetch_desc(&p.tma_b);
+    tma_prefetch_desc(&p.tma_out);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);   // leader's: one arrive.expect_tx covering both CTAs' bytes
+      mbar_init(&empty_bar[i], 1);  // per CTA: one multicast commit
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);    // per CTA: one multicast commit
+      mbar_init(&tmem_empty[i], 16);  // leader's: 8 epilogue warps of each CTA
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
+        const int m0 = (tile / p.n_tiles) * (2 * BM) + static_cast<int>(rank) * BM;
+        const int n0 = (tile % p.n_tiles) * BN + static_cast<int>(rank) * (BN / 2);
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * kStageBytes;
+          const uint32_t lbar = smem_u32(&full_bar[stage]) & 0xFEFFFFFFu;  // the leader's copy
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * kStageBytes);
+          tma_load_2d_pair(sa, &p.tma_a, lbar, kb * BK, m0);
+          tma_load_2d_pair(sa + kBytesA, &p.tma_b, lbar, kb * BK, n0);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // -------------------------------------------------------------- MMA issuer (leader only)
+    if (leader && lane == 0) {
+      // kind::f16: D fp32, A/B bf16 K-major, N = 256, M = 256 (pair)
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(BN >> 3) << 17) |
+                                 (static_cast<uint32_t>((2 * BM) >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+          const uint64_t da = desc_sw128(sa);
+          const uint64_t db = desc_sw128(sa + kBytesA);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_bf16_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_pair(&empty_bar[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_pair(&tmem_full[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue (both CTAs)
+    constexpr int kChunks = BN / 64;
+    const int ep_tid = threadIdx.x - 64;
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int row = quad * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    uint32_t chunk_ctr = 0;
+    for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
+      const int m0 = (tile / p.n_tiles) * (2 * BM) + static_cast<int>(rank) * BM;
+      const int n0 = (tile % p.n_tiles) * BN;
+      warp_mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN);
+#pragma unroll 1
+      for (int c = 0; c < kChunks; ++c, ++chunk_ctr) {
+        uint8_t* buf = staging + (chunk_ctr & 1) * kStagingBytes;
+        if (ep_tid == 0) tma_store_wait_read<1>();
+        named_bar_sync(1, 256);
+        const int ncol0 = n0 + c * 64;
+        uint8_t* my_row = buf + row * 128;
+        uint32_t r[32];
+        tmem_ld_32x32(t_row + static_cast<uint32_t>(c * 64 + half * 32), r);
+        tmem_ld_wait();
+        if (c == kChunks - 1) {  // accumulator fully read: hand the stage back to the leader's MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(mapa_rank0(smem_u32(&tmem_empty[acc])));
+        }
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const int n = ncol0 + half * 32 + i;
+          float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias != nullptr && n + 3 < p.N) b = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+          v[i + 0] = __uint_as_float(r[i + 0]) + b.x;
+          v[i + 1] = __uint_as_float(r[i + 1]) + b.y;
+          v[i + 2] = __uint_as_float(r[i + 2]) + b.z;
+          v[i + 3] = __uint_as_float(r[i + 3]) + b.w;
+        }
+        if (EPI == EPI_BF16_GELU) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = gelu_tanh(v[i]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 o;
+          o.x = pack_bf16(v[8 * j + 0], v[8 * j + 1]);
+          o.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+          o.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
+          o.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+          const int jj = half * 4 + j;
+          *reinterpret_cast<uint4*>(my_row + ((jj ^ (row & 7)) << 4)) = o;
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, 256);
+        if (ep_tid == 0) {
+          tma_store_2d(&p.tma_out, buf, ncol0, m0);
+          tma_store_commit();
+        }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if (ep_tid == 0) tma_store_wait<0>();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // the peer may still be signalling this CTA's barriers / reading its smem
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+template <int EPI>
+static int launch2(const Params& p, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm2_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) return set_error(-5, cudaGetErrorString(e));
+    configured = true;
+  }
+  const int tiles = p.m_tiles * p.n_tiles;
+  int clusters = num_sms() / 2;
+  if (tiles < clusters) clusters = tiles;
+  gemm2_kernel<EPI><<<2 * clusters, kThreads, kSmemBytes, stream>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(-6, cudaGetErrorString(e));
+  return 0;
+}
+
+}  // namespace g2
+
+bool gemm_2cta_applicable(int nseg, int64_t M, int64_t N, int epilogue) {
+  return nseg == 1 && (epilogue == g2::EPI_BF16 || epilogue == g2::EPI_BF16_GELU) && N % 256 == 0 &&
+         M >= 256 * 37;  // at least half a wave of 256-row tiles, otherwise the 1-CTA kernel balances better
+}
+
+int gemm_2cta_launch(const void* a, int64_t lda, const void* b, int64_t ldb, int64_t K, int64_t M, int64_t N,
+                     const float* bias, int epilogue, void* out, int64_t ldo, cudaStream_t stream) {
+  using namespace g2;
+  Params p;
+  p.kblocks = static_cast<int>((K + BK - 1) / BK);
+  p.M = static_cast<int>(M);
+  p.N = static_cast<int>(N);
+  p.m_tiles = static_cast<int>((M + 2 * BM - 1) / (2 * BM));
+  p.n_tiles = static_cast<int>(N / BN);
+  p.bias = bias;
+  int rc = make_tensor_map_2d(&p.tma_a, a, K, M, lda * 2, BK, BM, false);
+  if (rc) return rc;
+  rc = make_tensor_map_2d(&p.tma_b, b, K, N, ldb * 2, BK, BN / 2, false);
+  if (rc) return rc;
+  rc = make_tensor_map_2d(&p.tma_out, out, N, M, ldo * 2, 64, BM, false);
+  if (rc) return rc;
+  return epilogue == EPI_BF16 ? launch2<EPI_BF16>(p, stream) : launch2<EPI_BF16_GELU>(p, stream);
+}
+
+}  // namespace osudit

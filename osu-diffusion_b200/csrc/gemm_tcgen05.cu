@@ -18,6 +18,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <mutex>
 #include <unordered_map>
@@ -77,13 +78,13 @@ __device__ __forceinline__ constexpr uint32_t umma_idesc() {
 }
 
 __device__ __forceinline__ float gelu_tanh(float x) {
-  // 0.5 x (1 + tanh(u)) = x * sigmoid(2u) = x / (1 + 2^(-2 u log2 e)),
-  // u = sqrt(2/pi) (x + 0.044715 x^3): 4 FMA-pipe ops + ex2 + rcp per element.
-  constexpr float k1 = -2.0f * 0.7978845608028654f * 1.4426950408889634f;
-  constexpr float k3 = k1 * 0.044715f;
-  const float w = fmaf(x * x, k3, k1);
-  const float e = fast_exp2(x * w);
-  return __fdividef(x, 1.0f + e);
+  // 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3))) with the hardware tanh (one MUFU op per element;
+  // its 2^-11 error is far below the bf16 rounding of the result that follows)
+  const float u = x * fmaf(x * x, 0.044715f * 0.7978845608028654f, 0.7978845608028654f);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
 }
 
 // EPI_WGRAD: out[M,N] (fp32, reduce-added) += A[K,M]^T . B[K,N] with BOTH operands token-major
@@ -403,6 +404,15 @@ static int make_tensor_map(CUtensorMap* out, const void* ptr, uint64_t d0, uint6
   return make_tensor_map_nd(out, ptr, d0, d1, 0, stride_bytes, 0, b0, b1, is_f32);
 }
 
+int make_tensor_map_2d(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t stride_bytes,
+                       uint32_t b0, uint32_t b1, bool is_f32) {
+  return make_tensor_map_nd(out, ptr, d0, d1, 0, stride_bytes, 0, b0, b1, is_f32);
+}
+
+bool gemm_2cta_applicable(int nseg, int64_t M, int64_t N, int epilogue);
+int gemm_2cta_launch(const void* a, int64_t lda, const void* b, int64_t ldb, int64_t K, int64_t M, int64_t N,
+                     const float* bias, int epilogue, void* out, int64_t ldo, cudaStream_t stream);
+
 int make_tensor_map_3d(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2,
                        uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t b0, uint32_t b1) {
   return make_tensor_map_nd(out, ptr, d0, d1, d2, stride1_bytes, stride2_bytes, b0, b1, false);
@@ -438,6 +448,18 @@ extern "C" int osudit_gemm_bf16(int nseg, const void* const* a, const int64_t* l
   if (nseg < 1 || nseg > kMaxSeg) return set_error(-1, "gemm: nseg must be 1..3");
   if (M <= 0 || N <= 0 || (N % 8) != 0) return set_error(-1, "gemm: need M>0, N>0, N%8==0");
   if (epilogue < 0 || epilogue > 2) return set_error(-1, "gemm: unknown epilogue");
+  {
+    // large bf16-output GEMMs: CTA-pair kernel (gemm_2cta.cu); OSUDIT_GEMM_2CTA=0 forces the 1-CTA one
+    static const bool use_pair = [] {
+      const char* e = getenv("OSUDIT_GEMM_2CTA");
+      return !(e && e[0] == '0');
+    }();
+    if (use_pair && gemm_2cta_applicable(nseg, M, N, epilogue)) {
+      if (k[0] <= 0 || (k[0] % 8) != 0) return set_error(-1, "gemm: K must be a positive multiple of 8");
+      return gemm_2cta_launch(a[0], lda[0], b[0], ldb[0], k[0], M, N, bias, epilogue, out, ldo,
+                              static_cast<cudaStream_t>(stream));
+    }
+  }
   const int BN = (N % 256 == 0) ? 256 : 128;
   GemmParams p;
   p.nseg = nseg;

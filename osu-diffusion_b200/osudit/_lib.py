@@ -10,7 +10,7 @@ import os
 from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "libosudit.so")
+LIB_PATH = os.environ.get("OSUDIT_LIB") or os.path.join(os.path.dirname(_HERE), "libosudit.so")
 
 _P = c_void_p
 _I = c_int
