@@ -31,7 +31,7 @@ import torch  # noqa: E402
 
 MODEL, N_BEATMAPS, SEQ, STEPS_DIFF, CFG, BAND = "DiT-B", 64, 2048, 100, 1.5, 128
 METRIC = "beatmaps/sec DiT-B 100-step CFG sampling"
-NCU_GEMM_TRAFFIC_GB = 1.57  # ncu --set full, profiles/r01_summary.md: (1.558 + 0.762 + 1.962 + 2.003) / 4
+NCU_GEMM_TRAFFIC_GB = 1.59  # ncu --set full, profiles/r01b_summary.md: (1.562 + 0.764 + 1.964 + 2.069) / 4
 UNIT = "beatmaps/s"
 
 
@@ -266,17 +266,18 @@ def kernel_roofline(model, diffusion, zd, od, cd, yd, mask_d, device):
     af, ams, an = agg(rec["attn"])
     step_ms = sum(e0.elapsed_time(e1) for k in rec for e0, e1, _ in rec[k])
     ach = fl / (ms / 1e3) / 1e12
-    return {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (QKV, out-proj, fc1+GELU, fc2 launches)",
+    return {"bound": "tensor", "kernel": "g2::gemm2_kernel (cta_group::2 tcgen05 GEMM: QKV, out-proj, fc1+GELU, fc2 "
+            "launches)",
             "achieved": round(ach, 1), "peak": tf_peak, "unit": "TFLOP/s", "frac": round(ach / tf_peak, 4),
             "traffic": NCU_GEMM_TRAFFIC_GB, "traffic_unit": "GB per launch (dram read+write, mean of the QKV/out-proj/"
-            "fc1/fc2 launches in profiles/r01_summary.md; algorithmic 1.56)", "peak_source": src, "launches_timed": n,
+            "fc1/fc2 launches in profiles/r01b_summary.md; algorithmic 1.56)", "peak_source": src, "launches_timed": n,
             "avg_launch_ms": round(ms / max(n, 1), 4), "share_of_step": round(ms / step_ms, 3),
             "per_shape_tflops": {k: round(v[0] / (v[1] / 1e3) / 1e12, 1) for k, v in by_shape.items()},
             "hbm_kernel": {"kernel": "ln_modulate_kernel", "bound": "hbm",
                            "achieved": round(lb / (lms / 1e3) / 1e9, 1), "peak": hbm_peak, "unit": "GB/s",
                            "frac": round(lb / (lms / 1e3) / 1e9 / hbm_peak, 4), "launches_timed": ln_n,
                            "share_of_step": round(lms / step_ms, 3)},
-            "attention_kernel": {"kernel": "attn_band_kernel", "achieved": round(af / (ams / 1e3) / 1e12, 1),
+            "attention_kernel": {"kernel": "attn_tc::attn_window_kernel", "achieved": round(af / (ams / 1e3) / 1e12, 1),
                                  "unit": "TFLOP/s (banded algorithmic flops)", "share_of_step": round(ams / step_ms, 3)}}
 
 

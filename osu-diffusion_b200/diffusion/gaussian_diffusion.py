@@ -19,7 +19,7 @@ import math
 import numpy as np
 import torch as th
 
-from osudit import ops
+from osudit import graphs, ops
 
 
 class ModelMeanType(enum.Enum):
@@ -188,6 +188,13 @@ class GaussianDiffusion:
         assert t.shape == (B,)
         x = x.float().contiguous()
         t = t.long().contiguous()
+        if want_sample and not want_moments and denoised_fn is None and not th.is_grad_enabled() \
+                and graphs.eligible(x):
+            native = _native_dit(model)
+            if native is not None:  # launch-bound sizes: replay the whole step as one CUDA graph
+                sample, x0 = graphs.step(self, native[0], native[1], x, t, dict(model_kwargs or {}),
+                                         clip_denoised)
+                return dict(sample=sample, pred_xstart=x0, mean=None, log_variance=None)
         raw, cfg_half, cfg_scale = self._model_output(model, x, t, model_kwargs)
         assert raw.shape == (B, C * 2, *x.shape[2:])
         tb = self._tables(x.device)

@@ -137,7 +137,9 @@ def test_constructor_init_is_zero_output():
 
 def _patched_noise(monkeypatch, noises):
     import diffusion.gaussian_diffusion as gd
+    from osudit import graphs
     it = iter(noises)
+    monkeypatch.setattr(graphs, "_ENABLED", False)  # a captured step draws its noise inside the graph
     monkeypatch.setattr(gd.th, "randn_like", lambda x: next(it).to(x.device))
 
 
@@ -205,3 +207,43 @@ def test_free_running_100_steps_damped_fixture(monkeypatch):
           f"frac>0.5 {float((dist > 0.5).float().mean()):.3f}")
     assert float(dist.median()) < 0.5
     assert float((dist > 0.5).float().mean()) < 0.25
+
+
+@pytest.mark.parametrize("use_cfg", [True, False])
+@torch.no_grad()
+def test_cuda_graph_step_equals_eager(monkeypatch, use_cfg):
+    """The captured step (osudit/graphs.py) replays exactly the eager launches: same seed -> the same
+    bits, including the in-graph noise draw, across a whole respaced loop and after a weight update."""
+    from diffusion import create_diffusion
+    from osudit import graphs
+    shape, sd, m = build("DiT-S")
+    T, n = 256, 1
+    z, o, c, y = synth.sampling_batch(n, T, seed=0)
+    if not use_cfg:
+        z, o, c, y = z[:n], o[:n], c[:n], y[:n]
+    od, cd, yd, maskd = to_dev(o, c, y, synth.band_mask(T, 128))
+    d = create_diffusion("10", noise_schedule="squaredcos_cap_v2")
+    kw = dict(o=od, c=cd, y=yd, attn_mask=maskd)
+    fn = m.forward
+    if use_cfg:
+        kw["cfg_scale"] = 1.5
+        fn = m.forward_with_cfg
+
+    def run(enabled):
+        monkeypatch.setattr(graphs, "_ENABLED", enabled)
+        torch.manual_seed(5)
+        outs = [r for r in d.p_sample_loop_progressive(fn, z.shape, z.to(DEV), model_kwargs=kw, device=DEV)]
+        return torch.stack([r["sample"] for r in outs]), torch.stack([r["pred_xstart"] for r in outs])
+
+    graphs._cache.clear()
+    eager = run(False)
+    replay = run(True)
+    assert len(graphs._cache) == 1
+    assert torch.equal(eager[0], replay[0]) and torch.equal(eager[1], replay[1])
+    # a parameter update invalidates the capture (the packed bf16 copies are baked into it)
+    m.final_layer.linear.bias.add_(0.25)  # in-place under no_grad, like an optimizer step: bumps _version
+    eager2 = run(False)
+    replay2 = run(True)
+    assert torch.equal(eager2[0], replay2[0])
+    assert not torch.equal(eager2[1], eager[1])
+    graphs._cache.clear()

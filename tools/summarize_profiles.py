@@ -11,8 +11,11 @@ out = open(os.path.join(ROOT, "profiles", f"{tag}_summary.md"), "w")
 def w(*a): print(*a, file=out)
 
 w(f"# ncu summary `{tag}` — DiT-B, 64 beatmaps x 2048 datapoints (128 model rows), CFG, band W=128")
-w("\nCommand profiled: `python tools/profile_step.py 64 3` (three denoising steps, BASELINE config 2 shape) on one B200,")
-w("`--clock-control none`. Launch-list times are cold-cache and serialised: compare SHARES, not absolutes.\n")
+w("\nLaunch list: `ncu --metrics gpu__time_duration.sum --clock-control none -s 2000 -c 400 python bench.py --steps 1")
+w("--warmup 1` (launches 2000-2399 of the bench's own sampling loop, ~4 denoising steps). `--set full` captures: the")
+w("same model/shape through `python tools/profile_step.py 64 2` (two denoising steps) so that the replayed kernels are")
+w("reached quickly. One B200, `--clock-control none`. ncu times are cold-cache and serialised: compare SHARES with")
+w("bench.py's live `share_of_step`, not absolutes.\n")
 
 lines = [l for l in open(launches) if not l.startswith("==")]
 agg = collections.defaultdict(lambda: [0, 0.0])
