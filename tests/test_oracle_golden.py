@@ -150,3 +150,22 @@ def test_training_losses_and_grads(golden_dir, tag, l1):
     assert _rel(sd["final_layer.linear.weight"].grad, g[f"{tag}.grad.final_w"]) < 1e-4
     assert _rel(sd["blocks.0.attn.in_proj_weight"].grad, g[f"{tag}.grad.qkv0"]) < 1e-4
     assert _rel(sd["xoc_embedder.mlp.0.weight"].grad, g[f"{tag}.grad.first_w"]) < 1e-4
+
+
+def test_eager_library_restatement_matches_oracle():
+    """oracle/eager_cuda.py (the stock-torch call sequence timed on the GPU as 'the real bar') computes the
+    same function as the pinned oracle, with and without the band mask and CFG."""
+    from oracle import eager_cuda
+    shape = odit.shape_of("DiT-S")
+    sd = odit.init_state_dict(shape, seed=3, zero_init_std=0.02)
+    T = 96
+    z, o, c, y = synth.sampling_batch(1, T, seed=1)
+    t = torch.tensor([700, 31])
+    mask = synth.band_mask(T, 16)
+    for mk in (None, mask):
+        a = eager_cuda.forward(sd, shape.heads, z, t, o, c, y, mk)
+        b = odit.forward(sd, shape.heads, z, t, o, c, y, mk)
+        assert _rel(a, b) < 1e-5
+    a = eager_cuda.forward_with_cfg(sd, shape.heads, z, t, o, c, y, 1.5, mask)
+    b = odit.forward_with_cfg(sd, shape.heads, z, t, o, c, y, 1.5, mask)
+    assert _rel(a, b) < 1e-5
