@@ -181,6 +181,50 @@ int osudit_diffusion_loss(const float* model_out, const float* x0, const float* 
 /* out[b, :] = in[b, :] * g[b] (chain rule through the per-sample loss). */
 int osudit_scale_rows(const float* in, const float* g, int B, int64_t per_row, float* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * fp32 mode (north star: eps within 1e-5 relative L2 of the fp32 reference).  Activations stay fp32;
+ * a GEMM operand is the three-way bf16 split v = hi + mid + lo stored as one row [hi(K)|mid(K)|lo(K)]
+ * ("split3", bf16 [rows, 3K]); weights are stored [hi hi hi mid mid lo] ([N, 6K]) so that three
+ * K-segments of osudit_gemm_bf16 (widths 3K, 2K, K) accumulate the six significant products.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* osudit_gemm_bf16 with EPI_F32 and "precise" accumulation: the tensor core adds into its fp32 accumulator
+ * with truncation, a bias that grows with the length of the accumulation chain (measured 4e-6 relative at
+ * 200 MMAs).  Here the concatenated K range of all segments is cut into chains of kb_per_split 64-wide
+ * k-blocks; each chain's partial tile is added into `out` (zeroed by this call) with round-to-nearest fp32
+ * reduce-adds (cp.reduce.async.bulk).  bias is added once. */
+int osudit_gemm_bf16_splitk(int nseg, const void* const* a, const int64_t* lda, const void* const* b,
+                            const int64_t* ldb, const int64_t* k, int64_t M, int64_t N, const float* bias,
+                            int kb_per_split, float* out, int64_t ldo, void* stream);
+
+/* out3[r] = split3(act(in[r, :] (+ table[y[r], :]))), in fp32 [rows, K]; act 0 identity, 1 GELU(tanh)
+ * (models.py:138), 2 SiLU (models.py:30,148,189); table/y: the label-embedding add of models.py:320. */
+int osudit_split3_bf16(const float* in, int64_t rows, int K, int act, const float* table, const int64_t* y,
+                       void* out3, void* stream);
+
+/* osudit_ln_modulate with an fp32 branch (x updated in place) and a split3 result h3 bf16 [rows, 3D];
+ * any D % 4 == 0; the reference's operation order without contraction (models.py:12-13,160-163). */
+int osudit_ln_modulate_f32(float* x, const float* branch, const float* gate, const float* shift,
+                           const float* scale, int64_t mod_ld, int64_t rows, int T, int D, void* h3,
+                           void* stream);
+
+/* osudit_final_layer with an fp32 branch (models.py:192-196,323-324). */
+int osudit_final_layer_f32(float* x, const float* branch, const float* gate, const float* shift,
+                           const float* scale, int64_t mod_ld, int64_t rows, int T, int D, const float* w,
+                           const float* bias, int out_channels, float* out, void* stream);
+
+/* osudit_attn_band on fp32 qkv [B*T, 3*H*head_dim] -> fp32 out [B*T, H*head_dim], computed in fp32 on the
+ * CUDA cores (head_dim 64 or 72; band, full (w = -1) or generic mask as osudit_attn_band). */
+int osudit_attn_band_f32(const float* qkv, float* out, int B, int T, int H, int head_dim, int w_left,
+                         int w_right, const uint8_t* mask, void* stream);
+
+/* osudit_embed_xoc / osudit_timestep_features writing the fp32 feature rows unsplit:
+ * a fp32 [B*T, 384 + E]; out fp32 [rows, 256]. */
+int osudit_embed_xoc_f32(const float* x, const float* o, const float* c, const float* freqs64, float pf_x,
+                         float pf_y, int B, int xrows, int T, int E, float* a, void* stream);
+int osudit_timestep_features_f32(const int64_t* t, const float* freqs128, int rows, float* out,
+                                 void* stream);
+
 #ifdef __cplusplus
 }
 #endif

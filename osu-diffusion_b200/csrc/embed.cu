@@ -21,7 +21,12 @@
 
 namespace osudit {
 
+// lo == nullptr: `hi` is really a float* (fp32 mode, fp32_mode.cu) and receives v unsplit.
 __device__ __forceinline__ void split_store(__nv_bfloat16* hi, __nv_bfloat16* lo, int64_t idx, float v) {
+  if (lo == nullptr) {
+    reinterpret_cast<float*>(hi)[idx] = v;
+    return;
+  }
   const __nv_bfloat16 h = __float2bfloat16_rn(v);
   hi[idx] = h;
   lo[idx] = __float2bfloat16_rn(v - __bfloat162float(h));
@@ -155,6 +160,19 @@ extern "C" int osudit_timestep_features(const int64_t* t, const float* freqs128,
       t, freqs128, rows, static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo));
   OSUDIT_CHECK_LAUNCH();
   return 0;
+}
+
+extern "C" int osudit_embed_xoc_f32(const float* x, const float* o, const float* c, const float* freqs64,
+                                    float pf_x, float pf_y, int B, int xrows, int T, int E, float* a,
+                                    void* stream) {
+  if (a == nullptr) return set_error(-1, "embed_xoc_f32: null output");
+  return osudit_embed_xoc(x, o, c, freqs64, pf_x, pf_y, B, xrows, T, E, a, nullptr, stream);
+}
+
+extern "C" int osudit_timestep_features_f32(const int64_t* t, const float* freqs128, int rows, float* out,
+                                            void* stream) {
+  if (out == nullptr) return set_error(-1, "timestep_features_f32: null output");
+  return osudit_timestep_features(t, freqs128, rows, out, nullptr, stream);
 }
 
 extern "C" int osudit_silu_split(const float* a, const int32_t* a_index, const float* table,

@@ -43,7 +43,10 @@ struct GemmParams {
   int nseg;
   int M, N;
   int m_tiles, n_tiles;
-  int k_splits, kb_per_split;  // EPI_WGRAD: the K range (token dimension) is split across CTAs
+  // EPI_WGRAD: the K range (token dimension) is split across CTAs.  EPI_F32 with k_splits > 1 ("precise"
+  // accumulation, osudit_gemm_bf16_splitk): the concatenated k-block sequence of all segments is cut into
+  // short chains whose partial tiles are reduce-added in fp32 (round-to-nearest) into a zeroed output.
+  int k_splits, kb_per_split;
   const float* bias;
 };
 
@@ -116,7 +119,8 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_tiles = p.m_tiles * p.n_tiles * (kWgrad ? p.k_splits : 1);  // work items
+  const int total_tiles = p.m_tiles * p.n_tiles * p.k_splits;  // work items
+  const bool splitk = !kWgrad && p.k_splits > 1;
   int total_kblocks = 0;
   for (int s = 0; s < p.nseg; ++s) total_kblocks += p.kblocks[s];
 
@@ -151,7 +155,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
       int stage = 0;
       uint32_t phase = 0;
       for (int work = blockIdx.x; work < total_tiles; work += gridDim.x) {
-        const int tile = kWgrad ? work / p.k_splits : work;
+        const int tile = work / p.k_splits;
         const int m0 = (tile / p.n_tiles) * BM;
         const int n0 = (tile % p.n_tiles) * BN;
         if (kWgrad) {
@@ -172,8 +176,15 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
           }
           continue;
         }
+        int g_lo = 0, g_hi = total_kblocks;  // this work item's range of the concatenated k-blocks
+        if (splitk) {
+          g_lo = (work % p.k_splits) * p.kb_per_split;
+          g_hi = min(g_lo + p.kb_per_split, total_kblocks);
+        }
+        int g = 0;
         for (int s = 0; s < p.nseg; ++s) {
-          for (int kb = 0; kb < p.kblocks[s]; ++kb) {
+          for (int kb = 0; kb < p.kblocks[s]; ++kb, ++g) {
+            if (g < g_lo || g >= g_hi) continue;
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * C::kStageBytes;
             mbar_expect_tx(&full_bar[stage], C::kStageBytes);
@@ -201,6 +212,9 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
         if (kWgrad) {
           const int kb0 = (work % p.k_splits) * p.kb_per_split;
           n_kb = min(kb0 + p.kb_per_split, p.kblocks[0]) - kb0;
+        } else if (splitk) {
+          const int g_lo = (work % p.k_splits) * p.kb_per_split;
+          n_kb = min(g_lo + p.kb_per_split, total_kblocks) - g_lo;
         }
         for (int kb = 0; kb < n_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
@@ -245,9 +259,10 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
     uint32_t acc_phase = 0;
     uint32_t chunk_ctr = 0;
     for (int work = blockIdx.x; work < total_tiles; work += gridDim.x) {
-      const int tile = kWgrad ? work / p.k_splits : work;
+      const int tile = work / p.k_splits;
       const int m0 = (tile / p.n_tiles) * BM;
       const int n0 = (tile % p.n_tiles) * BN;
+      const bool add_bias = p.bias != nullptr && (work % p.k_splits) == 0;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
@@ -273,7 +288,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
         for (int i = 0; i < 32; i += 4) {
           const int n = ncol0 + half * 32 + i;
           float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.bias != nullptr && n + 3 < p.N) b = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+          if (add_bias && n + 3 < p.N) b = __ldg(reinterpret_cast<const float4*>(p.bias + n));
           v[i + 0] = __uint_as_float(r[i + 0]) + b.x;
           v[i + 1] = __uint_as_float(r[i + 1]) + b.y;
           v[i + 2] = __uint_as_float(r[i + 2]) + b.z;
@@ -304,7 +319,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
         fence_proxy_async_smem();
         named_bar_sync(1, kEpiThreads);
         if (ep_tid == 0) {
-          if (kWgrad) tma_reduce_add_2d(&p.tma_out, buf, ncol0, m0);
+          if (kWgrad || splitk) tma_reduce_add_2d(&p.tma_out, buf, ncol0, m0);
           else tma_store_2d(&p.tma_out, buf, ncol0, m0);
           tma_store_commit();
         }
@@ -429,7 +444,7 @@ static int launch(const GemmParams& p, cudaStream_t stream) {
     if (e != cudaSuccess) return set_error(-5, cudaGetErrorString(e));
     configured = true;
   }
-  const int tiles = p.m_tiles * p.n_tiles;
+  const int tiles = p.m_tiles * p.n_tiles * p.k_splits;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   kern<<<grid, 64 + epi_threads(EPI), C::kSmemBytes, stream>>>(p);
   cudaError_t e = cudaGetLastError();
@@ -441,10 +456,9 @@ static int launch(const GemmParams& p, cudaStream_t stream) {
 
 using namespace osudit;
 
-extern "C" int osudit_gemm_bf16(int nseg, const void* const* a, const int64_t* lda,
-                                const void* const* b, const int64_t* ldb, const int64_t* k,
-                                int64_t M, int64_t N, const float* bias, int epilogue, void* out,
-                                int64_t ldo, void* stream) {
+static int gemm_entry(int nseg, const void* const* a, const int64_t* lda, const void* const* b,
+                      const int64_t* ldb, const int64_t* k, int64_t M, int64_t N, const float* bias,
+                      int epilogue, void* out, int64_t ldo, void* stream, int kb_per_split) {
   if (nseg < 1 || nseg > kMaxSeg) return set_error(-1, "gemm: nseg must be 1..3");
   if (M <= 0 || N <= 0 || (N % 8) != 0) return set_error(-1, "gemm: need M>0, N>0, N%8==0");
   if (epilogue < 0 || epilogue > 2) return set_error(-1, "gemm: unknown epilogue");
@@ -454,7 +468,7 @@ extern "C" int osudit_gemm_bf16(int nseg, const void* const* a, const int64_t* l
       const char* e = getenv("OSUDIT_GEMM_2CTA");
       return !(e && e[0] == '0');
     }();
-    if (use_pair && gemm_2cta_applicable(nseg, M, N, epilogue)) {
+    if (use_pair && kb_per_split == 0 && gemm_2cta_applicable(nseg, M, N, epilogue)) {
       if (k[0] <= 0 || (k[0] % 8) != 0) return set_error(-1, "gemm: K must be a positive multiple of 8");
       return gemm_2cta_launch(a[0], lda[0], b[0], ldb[0], k[0], M, N, bias, epilogue, out, ldo,
                               static_cast<cudaStream_t>(stream));
@@ -483,6 +497,16 @@ extern "C" int osudit_gemm_bf16(int nseg, const void* const* a, const int64_t* l
   int rc = make_tensor_map(&p.tma_out, out, N, M, ldo * (f32 ? 4 : 2), f32 ? 32 : 64, BM, f32);
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (kb_per_split > 0) {  // precise accumulation: short tensor-core chains, fp32 reduce-add into zeros
+    if (!f32) return set_error(-1, "gemm_splitk: fp32 output only");
+    int total = 0;
+    for (int s = 0; s < nseg; ++s) total += p.kblocks[s];
+    p.kb_per_split = kb_per_split;
+    p.k_splits = (total + kb_per_split - 1) / kb_per_split;
+    cudaError_t e = cudaMemset2DAsync(out, static_cast<size_t>(ldo) * 4, 0, static_cast<size_t>(N) * 4,
+                                      static_cast<size_t>(M), st);
+    if (e != cudaSuccess) return set_error(-6, cudaGetErrorString(e));
+  }
   if (BN == 256) {
     if (epilogue == EPI_F32) return launch<256, EPI_F32>(p, st);
     if (epilogue == EPI_BF16) return launch<256, EPI_BF16>(p, st);
@@ -491,6 +515,21 @@ extern "C" int osudit_gemm_bf16(int nseg, const void* const* a, const int64_t* l
   if (epilogue == EPI_F32) return launch<128, EPI_F32>(p, st);
   if (epilogue == EPI_BF16) return launch<128, EPI_BF16>(p, st);
   return launch<128, EPI_BF16_GELU>(p, st);
+}
+
+extern "C" int osudit_gemm_bf16(int nseg, const void* const* a, const int64_t* lda,
+                                const void* const* b, const int64_t* ldb, const int64_t* k,
+                                int64_t M, int64_t N, const float* bias, int epilogue, void* out,
+                                int64_t ldo, void* stream) {
+  return gemm_entry(nseg, a, lda, b, ldb, k, M, N, bias, epilogue, out, ldo, stream, 0);
+}
+
+extern "C" int osudit_gemm_bf16_splitk(int nseg, const void* const* a, const int64_t* lda,
+                                       const void* const* b, const int64_t* ldb, const int64_t* k,
+                                       int64_t M, int64_t N, const float* bias, int kb_per_split,
+                                       float* out, int64_t ldo, void* stream) {
+  if (kb_per_split < 1) return set_error(-1, "gemm_splitk: kb_per_split must be >= 1");
+  return gemm_entry(nseg, a, lda, b, ldb, k, M, N, bias, EPI_F32, out, ldo, stream, kb_per_split);
 }
 
 // out[M,N] (fp32) += dY[rows,M]^T . X[rows,N]: the weight gradient of y = x W^T (W is [M,N] = [out,in]),

@@ -9,6 +9,8 @@ calling the model on CPU tensors raises.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -113,6 +115,9 @@ class DiT(nn.Module):
         self.initialize_weights()
         self._engine = None
         self._train_weights = None
+        # "bf16" (default: bf16 tensor-core operands, fp32 accumulate / residual / statistics; eps within 2e-3
+        # of the fp32 reference) or "fp32" (osudit/fp32.py: eps within 1e-5, inference only, ~8x slower)
+        self.precision = os.environ.get("OSUDIT_PRECISION", "bf16")
 
     def initialize_weights(self):
         """Same distributions as models.py:275-304 (xavier-uniform Linears with zero bias,
@@ -173,6 +178,8 @@ class DiT(nn.Module):
         native schedule in osudit/train.py; under no_grad it is the inference schedule."""
         if self._needs_grad():
             from osudit.train import DiTFunction, TrainWeights
+            if self.precision != "bf16":
+                raise NotImplementedError("precision='fp32' is an inference mode; train with precision='bf16'")
             for name, v in (("x", x), ("t", t), ("o", o), ("c", c), ("y", y)):
                 if not v.is_cuda:
                     raise RuntimeError(f"DiT.forward: `{name}` is on {v.device}; the native path runs "

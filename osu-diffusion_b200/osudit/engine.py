@@ -120,6 +120,7 @@ class DiTEngine:
         self.E = model.context_size
         self.hidden_mlp = model.blocks[0].mlp.fc1.weight.shape[0]
         self.weights = None
+        self._fp32 = None
         self._ws = {}
         self._freqs = {}
 
@@ -173,6 +174,14 @@ class DiTEngine:
     def forward(self, x, t, o, c, y, attn_mask=None, x_rows=None, mod=None):
         """Returns the raw model output fp32 [B, 4, T] (a workspace tensor, overwritten by the next
         call with the same shape).  x: [x_rows, 2, T] with x_rows in {B, B/2}."""
+        precision = getattr(self.model, "precision", "bf16")
+        if precision == "fp32":
+            if self._fp32 is None:
+                from .fp32 import Fp32Schedule
+                self._fp32 = Fp32Schedule(self)
+            return self._fp32.forward(x, t, o, c, y, attn_mask, x_rows)
+        if precision != "bf16":
+            raise ValueError(f"DiT.precision must be 'bf16' or 'fp32', got {precision!r}")
         B, T = o.shape
         D, H = self.D, self.H
         x_rows = B if x_rows is None else x_rows

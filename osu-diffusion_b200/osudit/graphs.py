@@ -79,7 +79,7 @@ def _key(diffusion, module, uses_cfg, x, kw, clip):
         return None if v is None else (v.data_ptr(), v._version, tuple(v.shape))
     return (id(diffusion), id(module), uses_cfg, tuple(x.shape), str(x.device), ident(kw["o"]), ident(kw["c"]),
             ident(kw["y"]), ident(kw.get("attn_mask")), float(kw.get("cfg_scale", 0.0)), bool(clip),
-            module.training)
+            module.training, getattr(module, "precision", "bf16"))
 
 
 def step(diffusion, module, uses_cfg, x, t, kw, clip):
