@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define OSUDIT_VERSION 1
+#define OSUDIT_VERSION 2
 
 int osudit_version(void);
 const char* osudit_last_error(void);
@@ -70,11 +70,12 @@ int osudit_attn_band(const void* qkv, void* out, int B, int T, int H, int head_d
 int osudit_gemm_wgrad(const void* dy, int64_t ld_dy, const void* x, int64_t ld_x, int64_t rows, int64_t M,
                       int64_t N, float* out, int64_t ldo, void* stream);
 
-/* dqkv (bf16 [B*T, 3*H*64]) from dout (bf16 [B*T, H*64]), the forward's qkv / out / lse.
- * delta is fp32 [B, H, T] scratch.  Band semantics as in osudit_attn_band; head_dim 64 only. */
+/* dqkv (bf16 [B*T, 3*H*hd]) from dout (bf16 [B*T, H*hd]), the forward's qkv / out / lse.
+ * delta is fp32 [B, H, T] scratch.  Band semantics as in osudit_attn_band; head_dim 64 or 72.
+ * dbias_qkv (fp32 [3*H*hd], ACCUMULATED, may be NULL) += column sums of dqkv: the in_proj_bias gradient. */
 int osudit_attn_band_bwd(const void* qkv, const void* out, const void* dout, const float* lse,
                          float* delta, void* dqkv, int B, int T, int H, int head_dim, int w_left,
-                         int w_right, void* stream);
+                         int w_right, float* dbias_qkv, void* stream);
 
 /* out[cols, out_ld] (bf16, out_ld >= rows: pad the GEMM K dimension to a multiple of 8) = in[rows, cols]^T;
  * in is bf16, or fp32 when in_is_f32. */
@@ -84,19 +85,33 @@ int osudit_transpose_bf16(const void* in, void* out, int64_t rows, int64_t cols,
 /* backward == 0: out = gelu_tanh(pre);  backward == 1: out = dy * gelu_tanh'(pre).  bf16, n % 8 == 0. */
 int osudit_gelu(const void* pre, const void* dy, void* out, int64_t n, int backward, void* stream);
 
+/* out[rows, N] = dy * gelu_tanh'(pre) and dbias[N] (fp32, ACCUMULATED, may be NULL) += column sums of out:
+ * the fc1 pre-activation gradient together with the fc1 bias gradient.  bf16, N % 8 == 0. */
+int osudit_gelu_bwd(const void* pre, const void* dy, void* out, int64_t rows, int N, float* dbias, void* stream);
+
 /* out[N] (fp32, ACCUMULATED: caller zeroes) += column sums of in[rows, N] (bf16 or fp32): bias grads. */
 int osudit_colsum(const void* in, int in_is_f32, int64_t rows, int N, float* out, void* stream);
 
 /* Backward of x_out = x + gate[b] * y (models.py:161-163,172):
- * dy (bf16) = gate[b] * dx;  dgate[b] (fp32, accumulated) += sum_t dx * y. */
+ * dy (bf16) = gate[b] * dx;  dgate[b] (fp32, accumulated) += sum_t dx * y;
+ * dbias[D] (fp32, ACCUMULATED, may be NULL) += column sums of dy: the bias gradient of the Linear that made y. */
 int osudit_gate_residual_bwd(const float* dx, const void* y, const float* gate, float* dgate,
-                             int64_t mod_ld, int B, int T, int D, void* dy, void* stream);
+                             int64_t mod_ld, int B, int T, int D, void* dy, float* dbias, void* stream);
 
 /* Backward of h = LayerNorm(x) * (1 + scale[b]) + shift[b] (models.py:12-13,160,173):
  * dshift[b], dscale[b] accumulated (fp32); dx written (accumulate == 0) or added to (== 1). */
 int osudit_ln_modulate_bwd(const float* x, const void* dh, const float* scale, float* dshift,
                            float* dscale, int64_t mod_ld, int B, int T, int D, float* dx,
                            int accumulate, void* stream);
+
+/* osudit_ln_modulate_bwd followed by osudit_gate_residual_bwd on the freshly updated dx, in one pass over the
+ * residual-stream gradient (the order the two occur in the backward of models.py:160-163,172-174):
+ * dx += LN-modulate-backward(x, dh);  then, when y != NULL (the output of the branch that was added to the
+ * residual right before this LayerNorm): dy (bf16) = gate[b] * dx, dgate[b] += sum_t dx * y,
+ * dbias[D] (may be NULL) += column sums of dy. */
+int osudit_ln_gate_bwd(const float* x, const void* dh, const float* scale, float* dshift, float* dscale,
+                       int64_t mod_ld, int B, int T, int D, float* dx, int accumulate, const void* y,
+                       const float* gate, float* dgate, void* dy, float* dbias, void* stream);
 
 /* Backward of FinalLayer (models.py:192-196) given dout fp32 [B,4,T] and x = the layer's input
  * (last gated residual already applied): dw [4,D], dbias [4], dshift/dscale accumulated; dx written. */

@@ -266,25 +266,55 @@ static int launch_band(const void* qkv, void* out, int B, int T, int H, int wl, 
 //   P = exp2(S * scale_log2 - lse),  delta = rowsum(dO * O),  dS = P * (dP - delta),
 //   dQ = scale * dS K,  dK = scale * dS^T Q,  dV = P^T dO,  with dP = dO V^T.
 // Two kernels so that no atomics are needed: one owns 64 queries (dQ), one owns 64 keys (dK, dV).
-// head_dim 64 only (the training configurations of BASELINE.json use DiT-B / DiT-L).
+// head_dim 64 and 72 (DiT-XL) share the code through Geo<HD>: for 72 the contraction over the head
+// dimension runs 5 k-steps with a zero padding chunk and the 10th output block is dropped.
 
 // delta[b, h, t] = sum_d dO[b, t, h, d] * O[b, t, h, d]
 __global__ void __launch_bounds__(256)
 attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout,
-                  float* __restrict__ delta, int64_t rows, int T, int H) {
+                  float* __restrict__ delta, int64_t rows, int T, int H, int HD) {
   const int lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int64_t b = row / T, t = row - b * T;
   for (int h = 0; h < H; ++h) {
-    const int64_t off = (row * H + h) * 64 + lane * 2;
-    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(o + off));
-    const float2 d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dout + off));
-    float v = a.x * d.x + a.y * d.y;
+    float v = 0.f;
+    for (int c = lane * 2; c < HD; c += 64) {
+      const int64_t off = (row * H + h) * HD + c;
+      const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(o + off));
+      const float2 d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dout + off));
+      v = fmaf(a.x, d.x, fmaf(a.y, d.y, v));
+    }
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
     if (lane == 0) delta[(b * H + h) * T + t] = v;
   }
+}
+
+// Column sums over the CTA's 64 rows of a [64 x HD] accumulator tile held as mma fragments (rows lane/4 and
+// lane/4 + 8 of each warp's 16, columns db*8 + (lane&3)*2 + {0,1}), added to dst[0..HD).  Must be called
+// by all 128 threads after the main loop's final __syncthreads (s_col aliases the dead tiles).
+template <int HD>
+__device__ __forceinline__ void tile_colsum(const float (&acc)[Geo<HD>::kDBlocks][4], float mul, float* s_col,
+                                            float* __restrict__ dst, int warp, int lane, int tid) {
+  using G = Geo<HD>;
+  if (tid < HD) s_col[tid] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int db = 0; db < G::kChunks; ++db) {
+    float c0 = acc[db][0] + acc[db][2], c1 = acc[db][1] + acc[db][3];
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) {
+      c0 += __shfl_xor_sync(0xffffffffu, c0, o);
+      c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+    }
+    if (lane < 4) {
+      atomicAdd(&s_col[db * 8 + lane * 2], c0);
+      atomicAdd(&s_col[db * 8 + lane * 2 + 1], c1);
+    }
+  }
+  __syncthreads();
+  if (tid < HD) atomicAdd(dst + tid, s_col[tid] * mul);
 }
 
 template <int HD>
@@ -292,9 +322,8 @@ __global__ void __launch_bounds__(128)
 attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout,
                    const float* __restrict__ lse, const float* __restrict__ delta,
                    __nv_bfloat16* __restrict__ dqkv, int T, int H, int wl, int wr, float scale_log2,
-                   float scale) {
+                   float scale, float* __restrict__ dbias) {
   using G = Geo<HD>;
-  static_assert(HD == 64, "backward is built for head_dim 64");
   extern __shared__ __align__(128) uint8_t smem_attn[];
   uint8_t* sQ = smem_attn;
   uint8_t* sdO = sQ + G::kTileBytes;
@@ -309,6 +338,11 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
   const __nv_bfloat16* gv = gq + 2 * D;
   const __nv_bfloat16* gdo = dout + static_cast<int64_t>(b) * T * D + h * HD;
 
+  if (G::kPadded) {  // zero the padding chunk of every row once; cp.async never writes it
+    for (int idx = tid; idx < 6 * kBKV; idx += 128)
+      *reinterpret_cast<uint4*>(smem_attn + (idx / kBKV) * G::kTileBytes + G::off(idx % kBKV, G::kChunks)) =
+          make_uint4(0, 0, 0, 0);
+  }
   const int kt_lo = max(0, q0 - wl) / kBKV;
   const int kt_hi = min(T - 1, min(q0 + kBQ - 1, T - 1) + wr) / kBKV;
   load_tile_async<HD>(sQ, gq, ld, q0, T, tid);
@@ -317,10 +351,10 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
   load_tile_async<HD>(sV[0], gv, ld, kt_lo * kBKV, T, tid);
   cp_async_commit();
 
-  float dq[HD / 8][4];
+  float dq[G::kDBlocks][4];
 #pragma unroll
-  for (int i = 0; i < HD / 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
-  uint32_t qf[HD / 16][4], dof[HD / 16][4];
+  for (int i = 0; i < G::kDBlocks; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
+  uint32_t qf[G::kKSteps][4], dof[G::kKSteps][4];
   const int qrow[2] = {q0 + warp * 16 + (lane >> 2), q0 + warp * 16 + (lane >> 2) + 8};
   float row_lse[2], row_delta[2];
 #pragma unroll
@@ -344,7 +378,7 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
     __syncthreads();
     if (kt == kt_lo) {
 #pragma unroll
-      for (int ks = 0; ks < HD / 16; ++ks) {
+      for (int ks = 0; ks < G::kKSteps; ++ks) {
         const int r = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
         const int ch = ks * 2 + (lane >> 4);
         ldmatrix_x4(qf[ks], smem_u32(sQ) + G::off(r, ch));
@@ -359,7 +393,7 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
     }
     const uint32_t sk = smem_u32(sK[buf]), sv = smem_u32(sV[buf]);
 #pragma unroll
-    for (int ks = 0; ks < HD / 16; ++ks) {
+    for (int ks = 0; ks < G::kKSteps; ++ks) {
 #pragma unroll
       for (int nb = 0; nb < kBKV / 8; nb += 2) {
         uint32_t kf[4], vf[4];
@@ -393,7 +427,7 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
       pf[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
       pf[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
 #pragma unroll
-      for (int db = 0; db < HD / 8; db += 2) {
+      for (int db = 0; db < G::kDBlocks; db += 2) {
         uint32_t kf[4];
         const int r = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
         const int ch = db + (lane >> 4);
@@ -409,10 +443,12 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
   for (int rr = 0; rr < 2; ++rr) {
     if (qrow[rr] >= T) continue;
 #pragma unroll
-    for (int db = 0; db < HD / 8; ++db)
+    for (int db = 0; db < G::kChunks; ++db)
       *reinterpret_cast<uint32_t*>(gdq + static_cast<int64_t>(qrow[rr]) * ld + db * 8 + (lane & 3) * 2) =
           pack_bf16(dq[db][2 * rr] * scale, dq[db][2 * rr + 1] * scale);
   }
+  if (dbias != nullptr)  // in_proj_bias gradient, q part (rows >= T contribute exact zeros)
+    tile_colsum<HD>(dq, scale, reinterpret_cast<float*>(smem_attn), dbias + h * HD, warp, lane, tid);
 }
 
 template <int HD>
@@ -420,9 +456,8 @@ __global__ void __launch_bounds__(128)
 attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout,
                     const float* __restrict__ lse, const float* __restrict__ delta,
                     __nv_bfloat16* __restrict__ dqkv, int T, int H, int wl, int wr, float scale_log2,
-                    float scale) {
+                    float scale, float* __restrict__ dbias) {
   using G = Geo<HD>;
-  static_assert(HD == 64, "backward is built for head_dim 64");
   extern __shared__ __align__(128) uint8_t smem_attn[];
   uint8_t* sK = smem_attn;
   uint8_t* sV = sK + G::kTileBytes;
@@ -451,6 +486,11 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
       s_delta[buf * kBQ + tid] = q < T ? g_delta[q] : 0.f;
     }
   };
+  if (G::kPadded) {  // zero the padding chunk of every row once; cp.async never writes it
+    for (int idx = tid; idx < 6 * kBKV; idx += 128)
+      *reinterpret_cast<uint4*>(smem_attn + (idx / kBKV) * G::kTileBytes + G::off(idx % kBKV, G::kChunks)) =
+          make_uint4(0, 0, 0, 0);
+  }
   load_tile_async<HD>(sK, gk, ld, k0, T, tid);
   load_tile_async<HD>(sV, gv, ld, k0, T, tid);
   load_tile_async<HD>(sQ[0], gq, ld, qt_lo * kBQ, T, tid);
@@ -458,13 +498,13 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
   cp_async_commit();
   load_stats(0, qt_lo * kBQ);
 
-  float dk[HD / 8][4], dv[HD / 8][4];
+  float dk[G::kDBlocks][4], dv[G::kDBlocks][4];
 #pragma unroll
-  for (int i = 0; i < HD / 8; ++i) {
+  for (int i = 0; i < G::kDBlocks; ++i) {
     dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f;
     dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f;
   }
-  uint32_t kfr[HD / 16][4], vfr[HD / 16][4];
+  uint32_t kfr[G::kKSteps][4], vfr[G::kKSteps][4];
   const int krow[2] = {k0 + warp * 16 + (lane >> 2), k0 + warp * 16 + (lane >> 2) + 8};
 
   for (int qt = qt_lo; qt <= qt_hi; ++qt) {
@@ -481,7 +521,7 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
     __syncthreads();
     if (qt == qt_lo) {
 #pragma unroll
-      for (int ks = 0; ks < HD / 16; ++ks) {
+      for (int ks = 0; ks < G::kKSteps; ++ks) {
         const int r = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
         const int ch = ks * 2 + (lane >> 4);
         ldmatrix_x4(kfr[ks], smem_u32(sK) + G::off(r, ch));
@@ -497,7 +537,7 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
     }
     const uint32_t sq = smem_u32(sQ[buf]), sdo = smem_u32(sdO[buf]);
 #pragma unroll
-    for (int ks = 0; ks < HD / 16; ++ks) {
+    for (int ks = 0; ks < G::kKSteps; ++ks) {
 #pragma unroll
       for (int nb = 0; nb < kBQ / 8; nb += 2) {
         uint32_t qfr[4], dofr[4];
@@ -535,7 +575,7 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
 #pragma unroll
     for (int kk = 0; kk < kBQ / 16; ++kk) {
 #pragma unroll
-      for (int db = 0; db < HD / 8; db += 2) {
+      for (int db = 0; db < G::kDBlocks; db += 2) {
         uint32_t dofr[4], qfr[4];
         const int r = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
         const int ch = db + (lane >> 4);
@@ -555,11 +595,16 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
   for (int rr = 0; rr < 2; ++rr) {
     if (krow[rr] >= T) continue;
 #pragma unroll
-    for (int db = 0; db < HD / 8; ++db) {
+    for (int db = 0; db < G::kChunks; ++db) {
       const int64_t off = static_cast<int64_t>(krow[rr]) * ld + db * 8 + (lane & 3) * 2;
       *reinterpret_cast<uint32_t*>(gdk + off) = pack_bf16(dk[db][2 * rr] * scale, dk[db][2 * rr + 1] * scale);
       *reinterpret_cast<uint32_t*>(gdv + off) = pack_bf16(dv[db][2 * rr], dv[db][2 * rr + 1]);
     }
+  }
+  if (dbias != nullptr) {  // in_proj_bias gradient, k and v parts
+    float* s_col = reinterpret_cast<float*>(smem_attn);
+    tile_colsum<HD>(dk, scale, s_col, dbias + D + h * HD, warp, lane, tid);
+    tile_colsum<HD>(dv, 1.0f, s_col + 128, dbias + 2 * D + h * HD, warp, lane, tid);
   }
 }
 
@@ -591,38 +636,48 @@ extern "C" int osudit_attn_band(const void* qkv, void* out, int B, int T, int H,
   return launch_band<72>(qkv, out, B, T, H, w_left, w_right, mask, lse, st);
 }
 
+template <int HD>
+static int launch_bwd(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv, int B,
+                      int T, int H, int w_left, int w_right, float* dbias, cudaStream_t st) {
+  constexpr int smem_dq = 6 * Geo<HD>::kTileBytes;
+  constexpr int smem_dkv = 6 * Geo<HD>::kTileBytes + 4 * kBQ * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e =
+        cudaFuncSetAttribute(attn_bwd_dq_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dq);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_bwd_dkv_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dkv);
+    if (e != cudaSuccess) return set_error(-5, cudaGetErrorString(e));
+    configured = true;
+  }
+  const float scale = 1.0f / sqrtf(static_cast<float>(HD));
+  const float scale_log2 = 1.4426950408889634f * scale;
+  dim3 grid((T + kBQ - 1) / kBQ, H, B);
+  attn_bwd_dq_kernel<HD><<<grid, 128, smem_dq, st>>>(
+      static_cast<const __nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(dout), lse, delta,
+      static_cast<__nv_bfloat16*>(dqkv), T, H, w_left, w_right, scale_log2, scale, dbias);
+  OSUDIT_CHECK_LAUNCH();
+  attn_bwd_dkv_kernel<HD><<<grid, 128, smem_dkv, st>>>(
+      static_cast<const __nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(dout), lse, delta,
+      static_cast<__nv_bfloat16*>(dqkv), T, H, w_left, w_right, scale_log2, scale, dbias);
+  OSUDIT_CHECK_LAUNCH();
+  return 0;
+}
+
 extern "C" int osudit_attn_band_bwd(const void* qkv, const void* out, const void* dout, const float* lse,
                                     float* delta, void* dqkv, int B, int T, int H, int head_dim,
-                                    int w_left, int w_right, void* stream) {
-  if (head_dim != 64) return set_error(-1, "attn_band_bwd: only head_dim 64 is implemented");
+                                    int w_left, int w_right, float* dbias_qkv, void* stream) {
+  if (head_dim != 64 && head_dim != 72)
+    return set_error(-1, "attn_band_bwd: head_dim must be 64 (DiT-S/B/L) or 72 (DiT-XL)");
   if (B <= 0 || T <= 0 || H <= 0 || B > 65535 || H > 65535) return set_error(-1, "attn_band_bwd: bad shape");
   if (w_left < 0 || w_left > T) w_left = T;
   if (w_right < 0 || w_right > T) w_right = T;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int64_t rows = static_cast<int64_t>(B) * T;
   attn_delta_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, st>>>(
-      static_cast<const __nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(dout), delta, rows, T, H);
+      static_cast<const __nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(dout), delta, rows, T, H,
+      head_dim);
   OSUDIT_CHECK_LAUNCH();
-  constexpr int smem_dq = 6 * Geo<64>::kTileBytes;
-  constexpr int smem_dkv = 6 * Geo<64>::kTileBytes + 4 * kBQ * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_bwd_dq_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dq);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(attn_bwd_dkv_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dkv);
-    if (e != cudaSuccess) return set_error(-5, cudaGetErrorString(e));
-    configured = true;
-  }
-  const float scale = 1.0f / sqrtf(static_cast<float>(head_dim));
-  const float scale_log2 = 1.4426950408889634f * scale;
-  dim3 grid((T + kBQ - 1) / kBQ, H, B);
-  attn_bwd_dq_kernel<64><<<grid, 128, smem_dq, st>>>(
-      static_cast<const __nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(dout), lse, delta,
-      static_cast<__nv_bfloat16*>(dqkv), T, H, w_left, w_right, scale_log2, scale);
-  OSUDIT_CHECK_LAUNCH();
-  attn_bwd_dkv_kernel<64><<<grid, 128, smem_dkv, st>>>(
-      static_cast<const __nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(dout), lse, delta,
-      static_cast<__nv_bfloat16*>(dqkv), T, H, w_left, w_right, scale_log2, scale);
-  OSUDIT_CHECK_LAUNCH();
-  return 0;
+  if (head_dim == 64) return launch_bwd<64>(qkv, dout, lse, delta, dqkv, B, T, H, w_left, w_right, dbias_qkv, st);
+  return launch_bwd<72>(qkv, dout, lse, delta, dqkv, B, T, H, w_left, w_right, dbias_qkv, st);
 }

@@ -115,6 +115,51 @@ gelu_kernel(const __nv_bfloat16* __restrict__ pre, const __nv_bfloat16* __restri
   reinterpret_cast<uint4*>(out)[i] = o;
 }
 
+// out[r, c] = dy[r, c] * gelu'(pre[r, c]) and dbias[c] += sum_r out[r, c] (the fc1 bias gradient):
+// thread = 8 consecutive columns x kGeluRows rows, one atomic per column per CTA.
+constexpr int kGeluRows = 64;
+__global__ void __launch_bounds__(256)
+gelu_bwd_colsum_kernel(const __nv_bfloat16* __restrict__ pre, const __nv_bfloat16* __restrict__ dy,
+                       __nv_bfloat16* __restrict__ out, float* __restrict__ dbias, int64_t rows, int N) {
+  const int c = (blockIdx.x * 256 + threadIdx.x) * 8;
+  if (c >= N) return;
+  const int64_t r0 = static_cast<int64_t>(blockIdx.y) * kGeluRows;
+  const int64_t r1 = r0 + kGeluRows < rows ? r0 + kGeluRows : rows;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int64_t rb = r0; rb < r1; rb += 4) {
+    uint4 p[4], g[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {  // 8 independent 16-byte loads in flight per thread
+      if (rb + j < r1) {
+        p[j] = *reinterpret_cast<const uint4*>(pre + (rb + j) * N + c);
+        g[j] = *reinterpret_cast<const uint4*>(dy + (rb + j) * N + c);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (rb + j >= r1) break;
+      uint32_t* pp = reinterpret_cast<uint32_t*>(&p[j]);
+      uint32_t* gg = reinterpret_cast<uint32_t*>(&g[j]);
+      uint4 o;
+      uint32_t* oo = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 x = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&pp[k]));
+        const float2 d = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&gg[k]));
+        const float v0 = d.x * gelu_tanh_grad(x.x), v1 = d.y * gelu_tanh_grad(x.y);
+        acc[2 * k] += v0;
+        acc[2 * k + 1] += v1;
+        oo[k] = pack_bf16(v0, v1);
+      }
+      *reinterpret_cast<uint4*>(out + (rb + j) * N + c) = o;
+    }
+  }
+  if (dbias != nullptr) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) atomicAdd(dbias + c + k, acc[k]);
+  }
+}
+
 // ------------------------------------------------------------------------------- col sums
 // out[N] (fp32, accumulated with atomics; host zeroes) += sum over rows of in[rows, N].
 template <typename T>
@@ -135,13 +180,14 @@ colsum_kernel(const T* __restrict__ in, float* __restrict__ out, int64_t rows, i
 __global__ void __launch_bounds__(384)
 gate_residual_bwd_kernel(const float* __restrict__ dx, const __nv_bfloat16* __restrict__ y,
                          const float* __restrict__ gate, float* __restrict__ dgate, int64_t mod_ld,
-                         int T, int D, __nv_bfloat16* __restrict__ dy) {
+                         int T, int D, __nv_bfloat16* __restrict__ dy, float* __restrict__ dbias) {
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * 32;
   const int c = threadIdx.x * 4;
   if (c >= D) return;
   const float4 g = *reinterpret_cast<const float4*>(gate + static_cast<int64_t>(b) * mod_ld + c);
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);  // column sums of dy: the bias gradient of the Linear before
   const int t1 = t0 + 32 < T ? t0 + 32 : T;
   for (int t = t0; t < t1; ++t) {
     const int64_t off = (static_cast<int64_t>(b) * T + t) * D + c;
@@ -150,10 +196,16 @@ gate_residual_bwd_kernel(const float* __restrict__ dx, const __nv_bfloat16* __re
     const float2 y01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&yv.x));
     const float2 y23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&yv.y));
     acc.x += d.x * y01.x; acc.y += d.y * y01.y; acc.z += d.z * y23.x; acc.w += d.w * y23.y;
+    const float4 gd = make_float4(g.x * d.x, g.y * d.y, g.z * d.z, g.w * d.w);
+    bsum.x += gd.x; bsum.y += gd.y; bsum.z += gd.z; bsum.w += gd.w;
     uint2 o;
-    o.x = pack_bf16(g.x * d.x, g.y * d.y);
-    o.y = pack_bf16(g.z * d.z, g.w * d.w);
+    o.x = pack_bf16(gd.x, gd.y);
+    o.y = pack_bf16(gd.z, gd.w);
     *reinterpret_cast<uint2*>(dy + off) = o;
+  }
+  if (dbias != nullptr) {
+    atomicAdd(dbias + c + 0, bsum.x); atomicAdd(dbias + c + 1, bsum.y);
+    atomicAdd(dbias + c + 2, bsum.z); atomicAdd(dbias + c + 3, bsum.w);
   }
   float* dg = dgate + static_cast<int64_t>(b) * mod_ld + c;
   atomicAdd(dg + 0, acc.x); atomicAdd(dg + 1, acc.y); atomicAdd(dg + 2, acc.z); atomicAdd(dg + 3, acc.w);
@@ -240,6 +292,127 @@ ln_modulate_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restr
   for (int i = threadIdx.x; i < D; i += 256) {
     atomicAdd(gs + i, s_dshift[i]);
     atomicAdd(gc + i, s_dscale[i]);
+  }
+}
+
+// ------------------------------------------- LayerNorm-modulate backward + gated residual backward
+// The two steps that follow each other along the residual stream in the backward pass, in ONE pass over dx:
+//   dx_new = dx_old + LN-modulate-backward(x, dh)                     (as ln_modulate_bwd_kernel)
+//   dy     = gate[b] * dx_new,  dgate[b] += sum_t dx_new * y,  dbias += sum_rows dy   (as gate_residual_bwd)
+// where y / gate belong to the branch whose output was added to the residual just BEFORE this LayerNorm in
+// the forward.  18*D B/token instead of 14*D + 12*D for the two separate kernels.  One warp owns kRows
+// consecutive rows; the four per-column sums are kept in a warp-private shared-memory strip (plain
+// read-modify-write, no atomics), reduced over the CTA's 4 warps at the end: one global atomic per column
+// per CTA per sum.
+constexpr int kLgWarps = 4;
+constexpr int kLgRows = 8;  // rows per warp
+
+template <int NV, bool kGate>
+__global__ void __launch_bounds__(kLgWarps * 32)
+ln_gate_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dh,
+                   const float* __restrict__ scale, float* __restrict__ dshift, float* __restrict__ dscale,
+                   int64_t mod_ld, int T, float* __restrict__ dx_acc, int accumulate,
+                   const __nv_bfloat16* __restrict__ y, const float* __restrict__ gate,
+                   float* __restrict__ dgate, __nv_bfloat16* __restrict__ dy, float* __restrict__ dbias) {
+  constexpr int D = NV * 128;
+  constexpr int kArr = kGate ? 4 : 2;
+  extern __shared__ float s_strip[];  // [kLgWarps][kArr][D]
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int b = blockIdx.y;
+  float* mine = s_strip + warp * kArr * D;
+  for (int i = lane; i < kArr * D; i += 32) mine[i] = 0.f;
+  __syncwarp();
+  const float* sc = scale + static_cast<int64_t>(b) * mod_ld;
+  const float* gt = kGate ? gate + static_cast<int64_t>(b) * mod_ld : nullptr;
+  constexpr float inv_d = 1.0f / D;
+  const int t_begin = (blockIdx.x * kLgWarps + warp) * kLgRows;
+  for (int t = t_begin; t < t_begin + kLgRows && t < T; ++t) {
+    const int64_t row = static_cast<int64_t>(b) * T + t;
+    const float* xrow = x + row * D;
+    const __nv_bfloat16* dhrow = dh + row * D;
+    float* drow = dx_acc + row * D;
+    float4 v[NV], old[NV];
+    uint2 dv[NV], yv[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {  // all loads of the row in flight before the first reduction
+      const int c = (lane + 32 * i) * 4;
+      v[i] = *reinterpret_cast<const float4*>(xrow + c);
+      dv[i] = *reinterpret_cast<const uint2*>(dhrow + c);
+      if (accumulate) old[i] = *reinterpret_cast<const float4*>(drow + c);
+      if (kGate) yv[i] = *reinterpret_cast<const uint2*>(y + row * D + c);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    const float mean = warp_sum_b(s) * inv_d;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float a = v[i].x - mean, bb = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      q += (a * a + bb * bb) + (c * c + d * d);
+    }
+    const float rstd = rsqrtf(warp_sum_b(q) * inv_d + kLnEpsB);
+    float4 g[NV];
+    float sg = 0.f, sgn = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (lane + 32 * i) * 4;
+      const float2 d01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&dv[i].x));
+      const float2 d23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&dv[i].y));
+      const float4 s4 = __ldg(reinterpret_cast<const float4*>(sc + c));
+      v[i].x = (v[i].x - mean) * rstd; v[i].y = (v[i].y - mean) * rstd;
+      v[i].z = (v[i].z - mean) * rstd; v[i].w = (v[i].w - mean) * rstd;
+      float4 a = *reinterpret_cast<float4*>(mine + c);  // dshift
+      a.x += d01.x; a.y += d01.y; a.z += d23.x; a.w += d23.y;
+      *reinterpret_cast<float4*>(mine + c) = a;
+      a = *reinterpret_cast<float4*>(mine + D + c);  // dscale
+      a.x += d01.x * v[i].x; a.y += d01.y * v[i].y; a.z += d23.x * v[i].z; a.w += d23.y * v[i].w;
+      *reinterpret_cast<float4*>(mine + D + c) = a;
+      g[i] = make_float4(d01.x * (1.f + s4.x), d01.y * (1.f + s4.y), d23.x * (1.f + s4.z),
+                         d23.y * (1.f + s4.w));
+      sg += (g[i].x + g[i].y) + (g[i].z + g[i].w);
+      sgn += (g[i].x * v[i].x + g[i].y * v[i].y) + (g[i].z * v[i].z + g[i].w * v[i].w);
+    }
+    const float mg = warp_sum_b(sg) * inv_d;
+    const float mgn = warp_sum_b(sgn) * inv_d;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (lane + 32 * i) * 4;
+      float4 o = make_float4(rstd * (g[i].x - mg - v[i].x * mgn), rstd * (g[i].y - mg - v[i].y * mgn),
+                             rstd * (g[i].z - mg - v[i].z * mgn), rstd * (g[i].w - mg - v[i].w * mgn));
+      if (accumulate) { o.x += old[i].x; o.y += old[i].y; o.z += old[i].z; o.w += old[i].w; }
+      *reinterpret_cast<float4*>(drow + c) = o;
+      if (kGate) {
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(gt + c));
+        const float2 y01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&yv[i].x));
+        const float2 y23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&yv[i].y));
+        const float4 gd = make_float4(g4.x * o.x, g4.y * o.y, g4.z * o.z, g4.w * o.w);
+        uint2 pk;
+        pk.x = pack_bf16(gd.x, gd.y);
+        pk.y = pack_bf16(gd.z, gd.w);
+        *reinterpret_cast<uint2*>(dy + row * D + c) = pk;
+        float4 a = *reinterpret_cast<float4*>(mine + 2 * D + c);  // dgate
+        a.x += o.x * y01.x; a.y += o.y * y01.y; a.z += o.z * y23.x; a.w += o.w * y23.y;
+        *reinterpret_cast<float4*>(mine + 2 * D + c) = a;
+        a = *reinterpret_cast<float4*>(mine + 3 * D + c);  // dbias
+        a.x += gd.x; a.y += gd.y; a.z += gd.z; a.w += gd.w;
+        *reinterpret_cast<float4*>(mine + 3 * D + c) = a;
+      }
+    }
+  }
+  __syncthreads();
+  float* dst[4] = {dshift + static_cast<int64_t>(b) * mod_ld, dscale + static_cast<int64_t>(b) * mod_ld,
+                   kGate ? dgate + static_cast<int64_t>(b) * mod_ld : nullptr, kGate ? dbias : nullptr};
+#pragma unroll
+  for (int a = 0; a < kArr; ++a) {
+    if (dst[a] == nullptr) continue;
+    for (int c = threadIdx.x; c < D; c += kLgWarps * 32) {
+      float sum = 0.f;
+#pragma unroll
+      for (int w = 0; w < kLgWarps; ++w) sum += s_strip[(w * kArr + a) * D + c];
+      atomicAdd(dst[a] + c, sum);
+    }
   }
 }
 
@@ -384,6 +557,36 @@ struct LnBwdLauncher {
 };
 
 template <int NV>
+struct LnGateBwdLauncher {
+  static int run(const float* x, const __nv_bfloat16* dh, const float* scale, float* dshift, float* dscale,
+                 int64_t mod_ld, int B, int T, float* dx, int accumulate, const __nv_bfloat16* y,
+                 const float* gate, float* dgate, __nv_bfloat16* dy, float* dbias, cudaStream_t st) {
+    const bool with_gate = y != nullptr;
+    const int smem = kLgWarps * (with_gate ? 4 : 2) * NV * 128 * static_cast<int>(sizeof(float));
+    static bool configured = false;
+    if (!configured) {
+      cudaError_t e = cudaFuncSetAttribute(ln_gate_bwd_kernel<NV, true>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, kLgWarps * 4 * NV * 128 * 4);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(ln_gate_bwd_kernel<NV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 kLgWarps * 2 * NV * 128 * 4);
+      if (e != cudaSuccess) return set_error(-5, cudaGetErrorString(e));
+      configured = true;
+    }
+    dim3 grid((T + kLgWarps * kLgRows - 1) / (kLgWarps * kLgRows), B);
+    if (with_gate)
+      ln_gate_bwd_kernel<NV, true><<<grid, kLgWarps * 32, smem, st>>>(x, dh, scale, dshift, dscale, mod_ld, T, dx,
+                                                                     accumulate, y, gate, dgate, dy, dbias);
+    else
+      ln_gate_bwd_kernel<NV, false><<<grid, kLgWarps * 32, smem, st>>>(x, dh, scale, dshift, dscale, mod_ld, T, dx,
+                                                                      accumulate, nullptr, nullptr, nullptr, nullptr,
+                                                                      nullptr);
+    OSUDIT_CHECK_LAUNCH();
+    return 0;
+  }
+};
+
+template <int NV>
 struct FinalBwdLauncher {
   static int run(const float* x, const float* dout, const float* shift, const float* scale,
                  float* dshift, float* dscale, int64_t mod_ld, int B, int T, const float* w, float* dw,
@@ -428,6 +631,17 @@ extern "C" int osudit_gelu(const void* pre, const void* dy, void* out, int64_t n
   return 0;
 }
 
+extern "C" int osudit_gelu_bwd(const void* pre, const void* dy, void* out, int64_t rows, int N, float* dbias,
+                               void* stream) {
+  if (rows <= 0 || N <= 0 || (N % 8) != 0) return set_error(-1, "gelu_bwd: need rows > 0 and N a multiple of 8");
+  dim3 grid((N / 8 + 255) / 256, static_cast<unsigned>((rows + kGeluRows - 1) / kGeluRows));
+  gelu_bwd_colsum_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(pre), static_cast<const __nv_bfloat16*>(dy),
+      static_cast<__nv_bfloat16*>(out), dbias, rows, N);
+  OSUDIT_CHECK_LAUNCH();
+  return 0;
+}
+
 extern "C" int osudit_colsum(const void* in, int in_is_f32, int64_t rows, int N, float* out, void* stream) {
   if (rows <= 0 || N <= 0) return set_error(-1, "colsum: bad shape");
   const int rpc = 256;
@@ -440,11 +654,13 @@ extern "C" int osudit_colsum(const void* in, int in_is_f32, int64_t rows, int N,
 }
 
 extern "C" int osudit_gate_residual_bwd(const float* dx, const void* y, const float* gate, float* dgate,
-                                        int64_t mod_ld, int B, int T, int D, void* dy, void* stream) {
+                                        int64_t mod_ld, int B, int T, int D, void* dy, float* dbias,
+                                        void* stream) {
   if (B <= 0 || T <= 0 || D % 4 != 0 || D / 4 > 384) return set_error(-1, "gate_residual_bwd: bad shape");
   dim3 grid((T + 31) / 32, B);
   gate_residual_bwd_kernel<<<grid, 384, 0, static_cast<cudaStream_t>(stream)>>>(
-      dx, static_cast<const __nv_bfloat16*>(y), gate, dgate, mod_ld, T, D, static_cast<__nv_bfloat16*>(dy));
+      dx, static_cast<const __nv_bfloat16*>(y), gate, dgate, mod_ld, T, D, static_cast<__nv_bfloat16*>(dy),
+      dbias);
   OSUDIT_CHECK_LAUNCH();
   return 0;
 }
@@ -455,6 +671,19 @@ extern "C" int osudit_ln_modulate_bwd(const float* x, const void* dh, const floa
   if (B <= 0 || T <= 0 || B > 65535) return set_error(-1, "ln_modulate_bwd: bad shape");
   return dispatch_nv1<LnBwdLauncher>(D, x, static_cast<const __nv_bfloat16*>(dh), scale, dshift, dscale,
                                      mod_ld, B, T, dx, accumulate, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int osudit_ln_gate_bwd(const float* x, const void* dh, const float* scale, float* dshift,
+                                  float* dscale, int64_t mod_ld, int B, int T, int D, float* dx, int accumulate,
+                                  const void* y, const float* gate, float* dgate, void* dy, float* dbias,
+                                  void* stream) {
+  if (B <= 0 || T <= 0 || B > 65535) return set_error(-1, "ln_gate_bwd: bad shape");
+  if (y != nullptr && (gate == nullptr || dgate == nullptr || dy == nullptr))
+    return set_error(-1, "ln_gate_bwd: y needs gate, dgate and dy");
+  return dispatch_nv1<LnGateBwdLauncher>(D, x, static_cast<const __nv_bfloat16*>(dh), scale, dshift, dscale,
+                                         mod_ld, B, T, dx, accumulate, static_cast<const __nv_bfloat16*>(y), gate,
+                                         dgate, static_cast<__nv_bfloat16*>(dy), dbias,
+                                         static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int osudit_final_layer_bwd(const float* x, const float* dout, const float* shift,

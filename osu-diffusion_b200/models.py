@@ -186,7 +186,7 @@ class DiT(nn.Module):
                                        "on CUDA only and has no CPU fallback")
             if self._train_weights is None:
                 self._train_weights = TrainWeights()
-            tw = self._train_weights.refresh(self)
+            tw = self._train_weights  # re-packed inside DiTFunction (eagerly, or as part of the CUDA graph)
             return DiTFunction.apply(self, tw, x.detach().float().contiguous(), t.long().contiguous(),
                                      o.float().contiguous(), c.float().contiguous(),
                                      self._labels(y.long()).contiguous(), attn_mask, *self.parameters())

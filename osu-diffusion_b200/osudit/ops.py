@@ -234,12 +234,25 @@ def colsum(a, out):
     return out
 
 
-def gate_residual_bwd(dx, y, mod, dmod, gate_col, B, T, dy):
+def gelu_bwd(pre, dy, out, dbias=None):
+    """out = dy * gelu'(pre) (may alias dy); dbias (fp32 [N], accumulated) += column sums of out."""
+    rows, N = pre.shape
+    lib = _lib.load()
+    _lib.check(lib.osudit_gelu_bwd(_chk(pre, torch.bfloat16, "gelu_bwd.pre"), _chk(dy, torch.bfloat16, "gelu_bwd.dy"),
+                                   _chk(out, torch.bfloat16, "gelu_bwd.out"), rows, N,
+                                   _chk(dbias, torch.float32, "gelu_bwd.dbias") if dbias is not None else None,
+                                   _stream()), "osudit_gelu_bwd")
+    return out
+
+
+def gate_residual_bwd(dx, y, mod, dmod, gate_col, B, T, dy, dbias=None):
     D = dx.shape[1]
     lib = _lib.load()
     _lib.check(lib.osudit_gate_residual_bwd(_chk(dx, torch.float32, "grb.dx"), _chk(y, torch.bfloat16, "grb.y"),
                                             _off(mod, gate_col), _off(dmod, gate_col), mod.stride(0), B, T, D,
-                                            _chk(dy, torch.bfloat16, "grb.dy"), _stream()),
+                                            _chk(dy, torch.bfloat16, "grb.dy"),
+                                            _chk(dbias, torch.float32, "grb.dbias") if dbias is not None else None,
+                                            _stream()),
                "osudit_gate_residual_bwd")
     return dy
 
@@ -252,6 +265,23 @@ def ln_modulate_bwd(x, dh, mod, dmod, shift_col, scale_col, B, T, dx, accumulate
                                           mod.stride(0), B, T, D, _chk(dx, torch.float32, "lnb.dx"),
                                           int(accumulate), _stream()), "osudit_ln_modulate_bwd")
     return dx
+
+
+def ln_gate_bwd(x, dh, mod, dmod, shift_col, scale_col, B, T, dx, accumulate, y=None, gate_col=None, dy=None,
+                dbias=None):
+    """ln_modulate_bwd, then (when y is given) gate_residual_bwd on the updated dx, in one pass."""
+    D = x.shape[1]
+    lib = _lib.load()
+    has = y is not None
+    _lib.check(lib.osudit_ln_gate_bwd(
+        _chk(x, torch.float32, "lgb.x"), _chk(dh, torch.bfloat16, "lgb.dh"), _off(mod, scale_col),
+        _off(dmod, shift_col), _off(dmod, scale_col), mod.stride(0), B, T, D, _chk(dx, torch.float32, "lgb.dx"),
+        int(accumulate), _chk(y, torch.bfloat16, "lgb.y") if has else None,
+        _off(mod, gate_col) if has else None, _off(dmod, gate_col) if has else None,
+        _chk(dy, torch.bfloat16, "lgb.dy") if has else None,
+        _chk(dbias, torch.float32, "lgb.dbias") if (has and dbias is not None) else None, _stream()),
+        "osudit_ln_gate_bwd")
+    return dy if has else dx
 
 
 def final_layer_bwd(x, dout, mod, dmod, shift_col, scale_col, B, T, w, dw, dbias, dx):
@@ -277,13 +307,16 @@ def silu_bwd(a, ds, dcond, table=None, y=None, dtable=None):
     return dcond
 
 
-def attn_band_bwd(qkv, out, dout, lse, dqkv, B, T, H, head_dim, w_left=-1, w_right=-1):
+def attn_band_bwd(qkv, out, dout, lse, dqkv, B, T, H, head_dim, w_left=-1, w_right=-1, dbias=None):
+    """dbias (fp32 [3*H*head_dim], accumulated) receives the in_proj_bias gradient when given."""
     delta = torch.empty(B, H, T, dtype=torch.float32, device=qkv.device)
     lib = _lib.load()
     _lib.check(lib.osudit_attn_band_bwd(_chk(qkv, torch.bfloat16, "ab.qkv"), _chk(out, torch.bfloat16, "ab.out"),
                                         _chk(dout, torch.bfloat16, "ab.dout"), _chk(lse, torch.float32, "ab.lse"),
                                         delta.data_ptr(), _chk(dqkv, torch.bfloat16, "ab.dqkv"), B, T, H, head_dim,
-                                        w_left, w_right, _stream()), "osudit_attn_band_bwd")
+                                        w_left, w_right,
+                                        _chk(dbias, torch.float32, "ab.dbias") if dbias is not None else None,
+                                        _stream()), "osudit_attn_band_bwd")
     return dqkv
 
 

@@ -12,6 +12,9 @@ stream and into every parameter.
 """
 from __future__ import annotations
 
+import os
+import weakref
+
 import torch
 
 from . import ops
@@ -76,8 +79,8 @@ def forward_train(model, tw: TrainWeights, x, t, o, c, y, attn_mask):
     B, T = o.shape
     D, H, depth = model.hidden_size, model.num_heads, len(model.blocks)
     hd, E, dev = D // H, model.context_size, o.device
-    if hd != 64:
-        raise NotImplementedError("the native backward covers head_dim 64 (DiT-S/B/L); DiT-XL training is not built")
+    if hd not in (64, 72):
+        raise NotImplementedError("the native attention covers head_dim 64 (DiT-S/B/L) and 72 (DiT-XL)")
     rows = B * T
     spec = classify_mask(attn_mask, T)
     if spec.generic is not None:
@@ -175,31 +178,45 @@ def backward_train(model, tw: TrainWeights, S, dout):
                         fl.linear.weight.detach().float().contiguous(), grads[fl.linear.weight],
                         grads[fl.linear.bias], dx)
 
+    # Bias gradients are the column sums of the branch gradients and are accumulated by the kernels that
+    # produce those.  Along the residual stream each LayerNorm backward is fused with the gated-residual
+    # backward that follows it (ops.ln_gate_bwd); only the very first gate (last block's MLP) stands alone.
+    dy_buf, dh_buf = _e(rows, D, device=dev), _e(rows, D, device=dev)
+    last = model.blocks[depth - 1]
+    grads[last.mlp.fc2.bias] = z32(D)
+    dy2 = ops.gate_residual_bwd(dx, S["blocks"][depth - 1]["y2"], mod, dmod, 6 * D * (depth - 1) + 5 * D, B, T,
+                                dy_buf, dbias=grads[last.mlp.fc2.bias])
     for i in reversed(range(depth)):
         blk, bw, sv = model.blocks[i], tw.blocks[i], S["blocks"][i]
         base = 6 * D * i
         hidden = sv["pre"].shape[1]
-        # ---- MLP branch: x_out = xb + gate_mlp * y2
-        dy2 = ops.gate_residual_bwd(dx, sv["y2"], mod, dmod, base + 5 * D, B, T, _e(rows, D, device=dev))
+        # ---- MLP branch: x_out = xb + gate_mlp * y2 (dy2 = gate_mlp * dx is already in dy_buf)
         grads[blk.mlp.fc2.weight] = _wgrad(dy2, sv["u"], dev)
-        grads[blk.mlp.fc2.bias] = ops.colsum(dy2, z32(D))
         du = ops.gemm([dy2], [bw["fc2_wt"]], None, ops.EPI_BF16, _e(rows, hidden, device=dev))
-        dpre = ops.gelu(sv["pre"], du, dy=du)  # in place over du
+        grads[blk.mlp.fc1.bias] = z32(hidden)
+        dpre = ops.gelu_bwd(sv["pre"], du, du, dbias=grads[blk.mlp.fc1.bias])  # in place over du
         grads[blk.mlp.fc1.weight] = _wgrad(dpre, sv["h2"], dev)
-        grads[blk.mlp.fc1.bias] = ops.colsum(dpre, z32(hidden))
-        dh2 = ops.gemm([dpre], [bw["fc1_wt"]], None, ops.EPI_BF16, _e(rows, D, device=dev))
-        ops.ln_modulate_bwd(sv["xb"], dh2, mod, dmod, base + 3 * D, base + 4 * D, B, T, dx, True)
-        # ---- attention branch: xb = xa + gate_msa * y1
-        dy1 = ops.gate_residual_bwd(dx, sv["y1"], mod, dmod, base + 2 * D, B, T, dy2)  # reuse buffer
+        dh2 = ops.gemm([dpre], [bw["fc1_wt"]], None, ops.EPI_BF16, dh_buf)
+        # ---- LN2 backward into dx, then the attention branch's gate: xb = xa + gate_msa * y1
+        grads[blk.attn.out_proj.bias] = z32(D)
+        dy1 = ops.ln_gate_bwd(sv["xb"], dh2, mod, dmod, base + 3 * D, base + 4 * D, B, T, dx, True,
+                              y=sv["y1"], gate_col=base + 2 * D, dy=dy_buf, dbias=grads[blk.attn.out_proj.bias])
         grads[blk.attn.out_proj.weight] = _wgrad(dy1, sv["att"], dev)
-        grads[blk.attn.out_proj.bias] = ops.colsum(dy1, z32(D))
-        datt = ops.gemm([dy1], [bw["out_wt"]], None, ops.EPI_BF16, dh2)  # reuse buffer
+        datt = ops.gemm([dy1], [bw["out_wt"]], None, ops.EPI_BF16, dh_buf)
+        grads[blk.attn.in_proj_bias] = z32(3 * D)
         dqkv = ops.attn_band_bwd(sv["qkv"], sv["att"], datt, sv["lse"], _e(rows, 3 * D, device=dev), B, T, H,
-                                 D // H, spec.w_left, spec.w_right)
+                                 D // H, spec.w_left, spec.w_right, dbias=grads[blk.attn.in_proj_bias])
         grads[blk.attn.in_proj_weight] = _wgrad(dqkv, sv["h1"], dev)
-        grads[blk.attn.in_proj_bias] = ops.colsum(dqkv, z32(3 * D))
-        dh1 = ops.gemm([dqkv], [bw["qkv_wt"]], None, ops.EPI_BF16, datt)  # reuse buffer
-        ops.ln_modulate_bwd(sv["xa"], dh1, mod, dmod, base, base + D, B, T, dx, True)
+        dh1 = ops.gemm([dqkv], [bw["qkv_wt"]], None, ops.EPI_BF16, dh_buf)
+        # ---- LN1 backward into dx, then the previous block's MLP gate
+        if i > 0:
+            prev = model.blocks[i - 1]
+            grads[prev.mlp.fc2.bias] = z32(D)
+            dy2 = ops.ln_gate_bwd(sv["xa"], dh1, mod, dmod, base, base + D, B, T, dx, True,
+                                  y=S["blocks"][i - 1]["y2"], gate_col=base - D, dy=dy_buf,
+                                  dbias=grads[prev.mlp.fc2.bias])
+        else:
+            ops.ln_gate_bwd(sv["xa"], dh1, mod, dmod, base, base + D, B, T, dx, True)
 
     # ---- first layer: x0 = a W^T + b  (no gradient to the inputs)
     first = model.xoc_embedder.mlp[0]
@@ -232,20 +249,118 @@ def backward_train(model, tw: TrainWeights, S, dout):
     return [grads.get(p) if p.requires_grad else None for p in model.parameters()]
 
 
+class TrainGraph:
+    """CUDA-graph replay of one training step's model work for a fixed (model, batch shape, mask).
+
+    A config-3 step (DiT-B, 256 x 128 datapoints) is ~370 launches of 10-300 us each plus ~300 small
+    allocations: eager, the host needs longer to enqueue them than the GPU needs to run them.  Two graphs are
+    captured once — (weight re-pack + forward_train) and backward_train, sharing one memory pool so the saved
+    activations stay where the backward graph expects them — and replayed every step with only the inputs and
+    the incoming output gradient copied into static buffers.  The weight copies are rebuilt INSIDE the forward
+    graph from the live fp32 parameters (same addresses every step), so optimizer updates need no re-capture.
+    The returned gradient tensors are the graph's static buffers; autograd / DDP copy out of them (they never
+    take ownership because this object also references them).
+    """
+
+    def __init__(self, model, x, t, o, c, y, attn_mask):
+        dev = o.device
+        self.model, self.mask = model, attn_mask
+        self.inputs = [v.clone() for v in (x, t, o, c, y)]
+        self.tw = TrainWeights()
+        self.sig = self.signature(model)
+        self.pending = None  # weakref to the autograd ctx whose backward has not run yet
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side), torch.no_grad():  # eager warm-up: host-side caches, function attributes
+            self.tw.refresh(model)
+            out, S = forward_train(model, self.tw, *self.inputs, attn_mask)
+            backward_train(model, self.tw, S, torch.zeros_like(out))
+            del out, S
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self.g_fwd = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(self.g_fwd):
+            self.tw.sig = None
+            self.tw.refresh(model)
+            self.out, self.S = forward_train(model, self.tw, *self.inputs, attn_mask)
+        self.dout = torch.zeros_like(self.out)
+        self.g_bwd = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(self.g_bwd, pool=self.g_fwd.pool()):
+            self.grads = backward_train(model, self.tw, self.S, self.dout)
+
+    @staticmethod
+    def signature(model):
+        return tuple((p.data_ptr(), p.requires_grad) for p in model.parameters())
+
+    def busy(self):
+        if self.pending is None:
+            return False
+        if self.pending() is None:  # that forward's graph was dropped without a backward
+            self.pending = None
+            return False
+        return True
+
+    def run_forward(self, ctx, x, t, o, c, y):
+        for dst, src in zip(self.inputs, (x, t, o, c, y)):
+            dst.copy_(src)
+        self.g_fwd.replay()
+        try:
+            self.pending = weakref.ref(ctx)
+        except TypeError:
+            self.pending = None
+        return self.out.clone()
+
+    def run_backward(self, dout):
+        self.dout.copy_(dout)
+        self.g_bwd.replay()
+        self.pending = None
+        return self.grads
+
+
+_GRAPHS_ENABLED = os.environ.get("OSUDIT_CUDA_GRAPHS", "1") != "0"
+_train_graphs: dict = {}
+
+
+def _train_graph_for(model, x, t, o, c, y, attn_mask):
+    """The cached TrainGraph for this call, a new one, or None (disabled / saved activations still in use)."""
+    if not _GRAPHS_ENABLED or torch.cuda.is_current_stream_capturing():
+        return None
+    spec = classify_mask(attn_mask, o.shape[1])
+    key = (id(model), tuple(o.shape), str(o.device), spec.w_left, spec.w_right, spec.generic is not None)
+    g = _train_graphs.get(key)
+    if g is not None and g.sig != TrainGraph.signature(model):
+        g = None  # parameters moved or were (un)frozen: capture again
+    if g is None:
+        _train_graphs.pop(key, None)
+        while len(_train_graphs) >= 2:  # each graph pins its activations: keep at most two shapes alive
+            _train_graphs.pop(next(iter(_train_graphs)))
+        g = TrainGraph(model, x, t, o, c, y, attn_mask)
+        _train_graphs[key] = g
+        return g
+    return None if g.busy() else g
+
+
 class DiTFunction(torch.autograd.Function):
     """out = DiT(x, t, o, c, y) with parameter gradients from the native backward."""
 
     @staticmethod
     def forward(ctx, model, tw, x, t, o, c, y, attn_mask, *params):
+        ctx.model = model
+        ctx.graph = _train_graph_for(model, x, t, o, c, y, attn_mask)
+        if ctx.graph is not None:
+            return ctx.graph.run_forward(ctx, x, t, o, c, y)
+        tw.refresh(model)
         out, saved = forward_train(model, tw, x, t, o, c, y, attn_mask)
-        ctx.model, ctx.tw, ctx.saved = model, tw, saved
+        ctx.tw, ctx.saved = tw, saved
         return out
 
     @staticmethod
     def backward(ctx, dout):
         with torch.no_grad():
-            grads = backward_train(ctx.model, ctx.tw, ctx.saved, dout.float())
-        ctx.saved = None
+            if ctx.graph is not None:
+                grads = ctx.graph.run_backward(dout.float())
+            else:
+                grads = backward_train(ctx.model, ctx.tw, ctx.saved, dout.float())
+                ctx.saved = None
         return (None,) * 8 + tuple(grads)
 
 

@@ -57,6 +57,14 @@ def test_gelu_forward_backward():
     y.backward(dy.float())
     assert rel(ops.gelu(pre, torch.empty_like(pre)).float(), y) < 3e-3
     assert rel(ops.gelu(pre, torch.empty_like(pre), dy=dy).float(), x.grad) < 4e-3
+    # backward fused with the fc1 bias gradient (column sums), in place over dy, ragged row count
+    pre2, dy2 = bf(torch.randn(77, 3072, device=DEV) * 2), bf(torch.randn(77, 3072, device=DEV))
+    x2 = pre2.float().requires_grad_()
+    torch.nn.functional.gelu(x2, approximate="tanh").backward(dy2.float())
+    dbias = torch.ones(3072, device=DEV)
+    out = ops.gelu_bwd(pre2, dy2, dy2, dbias=dbias)
+    assert out.data_ptr() == dy2.data_ptr() and rel(out.float(), x2.grad) < 4e-3
+    assert rel(dbias - 1.0, x2.grad.sum(0)) < 2e-3
 
 
 @pytest.mark.parametrize("f32", [False, True])
@@ -87,13 +95,25 @@ def test_gate_residual_and_ln_modulate_backward(D):
     dmod = torch.zeros_like(mod)
     dx = dx_up.clone()
     ops.ln_modulate_bwd(x2.detach(), dh, mod.detach(), dmod, 0, D, B, T, dx, True)
-    dy = ops.gate_residual_bwd(dx, y, mod.detach(), dmod, 2 * D, B, T, torch.empty_like(y))
+    dbias = torch.full((D,), 0.5, device=DEV)  # accumulated into: the bias gradient of the Linear that made y
+    dy = ops.gate_residual_bwd(dx, y, mod.detach(), dmod, 2 * D, B, T, torch.empty_like(y), dbias=dbias)
     assert rel(dx, x.grad) < 1e-4
     assert rel(dy.float(), yf.grad) < 4e-3
+    assert rel(dbias - 0.5, yf.grad.sum(0)) < 1e-4
     assert rel(dmod[:, :D], mod.grad[:, :D]) < 1e-4            # shift
     assert rel(dmod[:, D:2 * D], mod.grad[:, D:2 * D]) < 1e-4  # scale
     assert rel(dmod[:, 2 * D:3 * D], mod.grad[:, 2 * D:3 * D]) < 1e-4  # gate
     assert float(dmod[:, 3 * D:].abs().max()) == 0.0
+    # the fused single pass (LN backward, then the gate on the updated dx) equals the two kernels above
+    dmod2, dx2, dbias2 = torch.zeros_like(mod), dx_up.clone(), torch.zeros(D, device=DEV)
+    dy2 = ops.ln_gate_bwd(x2.detach(), dh, mod.detach(), dmod2, 0, D, B, T, dx2, True, y=y, gate_col=2 * D,
+                          dy=torch.empty_like(y), dbias=dbias2)
+    assert rel(dx2, dx) < 1e-6 and rel(dy2.float(), dy.float()) < 1e-3
+    assert rel(dmod2, dmod) < 1e-5 and rel(dbias2, dbias - 0.5) < 1e-5
+    dmod3, dx3 = torch.zeros_like(mod), torch.full_like(dx_up, 9.0)
+    ops.ln_gate_bwd(x2.detach(), dh, mod.detach(), dmod3, 0, D, B, T, dx3, False)  # no gate, overwrite dx
+    assert rel(dx3, dx - dx_up) < 1e-5 and rel(dmod3[:, :2 * D], dmod[:, :2 * D]) < 1e-5
+    assert float(dmod3[:, 2 * D:].abs().max()) == 0.0
 
 
 @pytest.mark.parametrize("D", [384, 768])
@@ -116,9 +136,10 @@ def test_final_layer_backward(D):
         assert rel(got, want) < 1e-4
 
 
-@pytest.mark.parametrize("B,T,H,W", [(2, 128, 3, None), (1, 200, 2, None), (2, 300, 2, 128), (1, 512, 1, 40)])
-def test_attention_backward(B, T, H, W):
-    hd, D = 64, H * 64
+@pytest.mark.parametrize("B,T,H,W,hd", [(2, 128, 3, None, 64), (1, 200, 2, None, 64), (2, 300, 2, 128, 64),
+                                        (1, 512, 1, 40, 64), (2, 200, 2, None, 72), (1, 300, 3, 128, 72)])
+def test_attention_backward(B, T, H, W, hd):
+    D = H * hd
     qkv = bf(torch.randn(B * T, 3 * D, device=DEV))
     dout = bf(torch.randn(B * T, D, device=DEV))
     x = qkv.float().requires_grad_()
@@ -135,8 +156,10 @@ def test_attention_backward(B, T, H, W):
     assert rel(out.float(), ref) < 6e-3
     lse_ref = torch.logsumexp(s, -1) / math.log(2.0)
     assert float((lse - lse_ref).abs().max()) < 2e-2
-    dqkv = ops.attn_band_bwd(qkv, out, dout, lse, torch.empty_like(qkv), B, T, H, hd, wl, wr)
+    dbias = torch.zeros(3 * D, device=DEV)
+    dqkv = ops.attn_band_bwd(qkv, out, dout, lse, torch.empty_like(qkv), B, T, H, hd, wl, wr, dbias=dbias)
     g = x.grad
+    assert rel(dbias, g.sum(0)) < 1.2e-2  # in_proj_bias gradient = column sums of dqkv
     for name, sl in (("dq", slice(0, D)), ("dk", slice(D, 2 * D)), ("dv", slice(2 * D, 3 * D))):
         e = rel(dqkv[:, sl].float(), g[:, sl])
         assert e < 1.2e-2, (name, e)
@@ -217,6 +240,33 @@ def test_training_losses_and_parameter_gradients(name, B, T, use_l1):
     print(f"{name} B={B} T={T}: worst parameter-gradient rel-L2 {worst[1]:.2e} ({worst[0]})")
 
 
+def test_xl_geometry_parameter_gradients():
+    """DiT-XL geometry (hidden 1152, 16 heads of 72) at depth 2: the head_dim-72 attention backward and the
+    D = 1152 LayerNorm / GEMM shapes, against fp32 autograd of the oracle."""
+    import models
+    from diffusion import create_diffusion
+    shape = odit.DiTShape(depth=2, hidden=1152, heads=16)
+    sd = odit.init_state_dict(shape, seed=2, zero_init_std=0.05)
+    m = models.DiT(depth=2, hidden_size=1152, num_heads=16, num_classes=52670, context_size=144)
+    m.load_state_dict(sd, strict=True)
+    m = m.to(DEV).eval()
+    B, T = 2, 160
+    (x, o, c), y = synth.training_batch(B, T, seed=4)
+    g = torch.Generator().manual_seed(6)
+    noise, t = torch.randn(B, 2, T, generator=g), torch.tensor([0, 640])
+    sdg = {k: v.clone().requires_grad_(v.is_floating_point() and "playfield" not in k) for k, v in sd.items()}
+    s = odiff.Schedule("")
+    ref = odiff.training_losses(s, lambda x_t, tt: odit.forward(sdg, 16, x_t, tt, o, c, y), x, t, noise, use_l1=True)
+    ref["loss"].mean().backward()
+    d = create_diffusion("", noise_schedule="squaredcos_cap_v2", use_l1=True)
+    terms = d.training_losses(m, x.to(DEV), t.to(DEV), dict(o=o.to(DEV), c=c.to(DEV), y=y.to(DEV)), noise=noise.to(DEV))
+    torch.testing.assert_close(terms["l1"].detach().cpu(), ref["l1"].detach(), rtol=5e-3, atol=1e-4)
+    terms["loss"].mean().backward()
+    worst = max((rel(p.grad, sdg[k].grad), k) for k, p in m.named_parameters() if p.requires_grad)
+    print(f"XL geometry depth 2: worst parameter-gradient rel-L2 {worst[0]:.2e} ({worst[1]})")
+    assert worst[0] < 5e-2
+
+
 def test_one_optimizer_step_reduces_the_loss():
     """train.py:249-261 in miniature: fp16-autocast context + GradScaler + AdamW on the native path."""
     from diffusion import create_diffusion
@@ -238,6 +288,61 @@ def test_one_optimizer_step_reduces_the_loss():
         losses.append(float(loss))
     print("losses", losses)
     assert all(math.isfinite(v) for v in losses) and losses[-1] < losses[0]
+
+
+def test_cuda_graph_training_step_matches_eager(monkeypatch):
+    """osudit/train.py::TrainGraph replays the same launches as the eager schedule: same losses and gradients
+    (up to atomic / reduce-add ordering) over several optimizer steps, including the in-graph weight re-pack,
+    and a second forward before the first backward falls back to the eager path instead of clobbering it."""
+    import copy
+    from diffusion import create_diffusion
+    from osudit import train as otrain
+    B, T = 4, 128
+    shape, sd, m_g, (x, o, c, y, noise, t) = _train_setup("DiT-S", B, T)
+    m_e = copy.deepcopy(m_g)
+    d = create_diffusion("", noise_schedule="squaredcos_cap_v2", use_l1=True)
+    kw = dict(o=o.to(DEV), c=c.to(DEV), y=y.to(DEV))
+    opt = torch.optim.AdamW(m_g.parameters(), lr=1e-3, weight_decay=0)
+    otrain._train_graphs.clear()
+    losses = []
+    for step in range(4):
+        gen = torch.Generator().manual_seed(step)
+        tt = torch.randint(0, 1000, (B,), generator=gen).to(DEV)
+        nz = torch.randn(B, 2, T, generator=gen).to(DEV)
+        if step == 2:  # a large in-place weight change: the replayed graph must see it (in-graph re-pack)
+            with torch.no_grad():
+                m_g.blocks[0].mlp.fc1.weight.mul_(1.3)
+                m_g.final_layer.linear.weight.mul_(0.7)
+        m_e.load_state_dict(m_g.state_dict())  # identical fp32 weights on both sides, every step
+        out = {}
+        for m, enabled in ((m_g, True), (m_e, False)):
+            monkeypatch.setattr(otrain, "_GRAPHS_ENABLED", enabled)
+            loss = d.training_losses(m, x.to(DEV), tt, kw, noise=nz)["loss"].mean()
+            loss.backward()
+            out[enabled] = (float(loss), {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None})
+        m_e.zero_grad(set_to_none=True)
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        losses.append(out[True][0])
+        assert abs(out[True][0] - out[False][0]) < 1e-5 * abs(out[False][0]), (step, out[True][0], out[False][0])
+        worst = max((rel(out[True][1][k], out[False][1][k]), k) for k in out[False][1])
+        print(f"step {step}: loss {out[True][0]:.6f}, worst graph-vs-eager gradient rel-L2 {worst[0]:.2e} ({worst[1]})")
+        assert worst[0] < 5e-4, (step, worst)  # only atomic / reduce-add ordering (and bf16 re-rounding of it) differs
+    assert len(set(round(v, 5) for v in losses)) == 4
+    assert len(otrain._train_graphs) == 1
+    # two forwards in flight: the second must not overwrite the first one's saved activations
+    monkeypatch.setattr(otrain, "_GRAPHS_ENABLED", True)
+    l1 = d.training_losses(m_g, x.to(DEV), t.to(DEV), kw, noise=noise.to(DEV))["loss"].mean()
+    l2 = d.training_losses(m_g, x.to(DEV), (t + 1).clamp(max=999).to(DEV), kw, noise=noise.to(DEV))["loss"].mean()
+    l1.backward()
+    g1 = {k: p.grad.clone() for k, p in m_g.named_parameters() if p.grad is not None}
+    m_g.zero_grad(set_to_none=True)
+    l2.backward()
+    m_g.zero_grad(set_to_none=True)
+    monkeypatch.setattr(otrain, "_GRAPHS_ENABLED", False)
+    d.training_losses(m_g, x.to(DEV), t.to(DEV), kw, noise=noise.to(DEV))["loss"].mean().backward()
+    assert max(rel(g1[k], p.grad) for k, p in m_g.named_parameters() if p.grad is not None) < 1e-3
+    otrain._train_graphs.clear()
 
 
 def test_loss_curve_tracks_the_oracle():

@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared:
         assert hasattr(lib, name), name
-    assert _lib.load().osudit_version() == 1
+    assert _lib.load().osudit_version() == 2
 
 
 def test_no_reference_or_oracle_imports_in_product():
