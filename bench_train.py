@@ -65,7 +65,12 @@ def run_native(args, rank, world, local_rank):
     if world > 1:
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank])
     diffusion = create_diffusion("", noise_schedule="squaredcos_cap_v2", use_l1=True)
-    opt = torch.optim.AdamW(net.parameters(), lr=1e-4, weight_decay=0)
+    if args.fused_optimizer:  # opt-in: AdamW + EMA + unscale + inf-skip in one launch (osudit/optim.py)
+        from osudit.optim import FusedAdamWEMA
+        opt = FusedAdamWEMA(net.parameters(), lr=1e-4, weight_decay=0)
+        opt.attach_ema(ema, model, decay=0.9999)
+    else:
+        opt = torch.optim.AdamW(net.parameters(), lr=1e-4, weight_decay=0)
     scaler = torch.amp.GradScaler("cuda")
     B = args.global_batch // world
     (x, o, c), y = synth.training_batch(B, SEQ, seed=rank)
@@ -81,7 +86,8 @@ def run_native(args, rank, world, local_rank):
         scaler.step(opt)
         scaler.update()
         opt.zero_grad(set_to_none=True)
-        update_ema(ema, model)
+        if not args.fused_optimizer:
+            update_ema(ema, model)
         return loss
 
     def barrier():
@@ -117,6 +123,8 @@ def run_native(args, rank, world, local_rank):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"{args.model} training, seq-len {SEQ}, global batch {args.global_batch}, L1+VB loss, "
                                    "AdamW 1e-4, EMA, fp16-autocast context + GradScaler as train.py; DDP NCCL all-reduce",
+                       "optimizer": "osudit FusedAdamWEMA (opt-in)" if args.fused_optimizer
+                       else "torch.optim.AdamW + update_ema loop (train.py unchanged)",
                        "parallelism": f"dp{world}"},
             "model_tflops": round(flops_per_seq(args.model) * value / world / 1e12, 1),
             "gpu_launches": launches, "final_loss": round(final_loss, 4)}
@@ -167,6 +175,8 @@ def main():
     ap.add_argument("--model", default="DiT-B")
     ap.add_argument("--global-batch", type=int, default=256)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--fused-optimizer", action="store_true",
+                    help="use osudit.optim.FusedAdamWEMA instead of torch.optim.AdamW + the update_ema loop")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     line = run_reference(args, rank) if args.impl == "reference" else \

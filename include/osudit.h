@@ -197,6 +197,32 @@ int osudit_diffusion_loss(const float* model_out, const float* x0, const float* 
 int osudit_scale_rows(const float* in, const float* g, int B, int64_t per_row, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Optimizer step: one multi-tensor launch for AdamW + EMA + gradient unscale + skip on
+ * non-finite gradients.  Opt-in replacement of `scaler.step(opt)` with torch.optim.AdamW (train.py:154,
+ * 258-259) followed by `update_ema(ema, model.module)` (train.py:36-45,261).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct OsuditOptSeg {
+  float* p;       /* parameter (fp32), updated in place                         */
+  const float* g; /* its gradient (fp32), possibly still multiplied by grad_scale */
+  float* m;       /* exp_avg                                                    */
+  float* v;       /* exp_avg_sq                                                 */
+  float* ema;     /* the EMA copy of p, or NULL                                 */
+  long long n;    /* elements                                                   */
+} OsuditOptSeg;
+
+/* Elements per chunk: chunk c = (segment index, chunk offset within the segment) covers elements
+ * [offset * E, min((offset + 1) * E, n)). */
+int osudit_opt_chunk_elems(void);
+
+/* segs: DEVICE array of OsuditOptSeg; chunks: DEVICE array of nchunks (int32 segment, int32 offset) pairs.
+ * step (device fp32 scalar) is incremented first unless *found_inf != 0; then, unless *found_inf != 0, every
+ * element gets torch.optim.AdamW's update with g / *grad_scale and ema = ema*ema_decay + p_new*(1-ema_decay).
+ * grad_scale / found_inf may be NULL (no scaling / never skip). */
+int osudit_adamw_ema_step(const void* segs, const int32_t* chunks, int nchunks, float lr, float beta1,
+                          float beta2, float eps, float weight_decay, float ema_decay, float* step,
+                          const float* grad_scale, const float* found_inf, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * fp32 mode (north star: eps within 1e-5 relative L2 of the fp32 reference).  Activations stay fp32;
  * a GEMM operand is the three-way bf16 split v = hi + mid + lo stored as one row [hi(K)|mid(K)|lo(K)]
  * ("split3", bf16 [rows, 3K]); weights are stored [hi hi hi mid mid lo] ([N, 6K]) so that three

@@ -52,11 +52,12 @@ from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     for _ in range(3): phases(False)
     torch.cuda.synchronize()
-ka = prof.key_averages()
+from torch.autograd import DeviceType
+ka = [e for e in prof.key_averages() if e.device_type == DeviceType.CUDA]  # kernels / memcpys / memsets only
 tot = sum(e.device_time_total for e in ka) / 3 / 1e3
-print("GPU busy %.2f ms/step" % tot)
-for e in sorted(ka, key=lambda e: -e.device_time_total)[:14]:
-    print("  %-70s %8.3f ms  x%d" % (e.key[:70], e.device_time_total / 3 / 1e3, e.count // 3))
+print("GPU busy %.2f ms/step (sum of device activities)" % tot)
+for e in sorted(ka, key=lambda e: -e.device_time_total)[:45]:
+    print("  %-84s %8.3f ms  x%d" % (e.key[:84], e.device_time_total / 3 / 1e3, e.count // 3))
 
 if os.environ.get("OSUDIT_CPROFILE"):
     import cProfile, pstats
