@@ -347,6 +347,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: keep the real stdout aside and point fd 1 at stderr, so that anything a
+    # library writes to C stdout (NCCL prints its version banner there when NCCL_DEBUG is set) cannot precede it
+    sys.stdout.flush()
+    out_fd = os.dup(1)
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
@@ -357,7 +362,7 @@ def main():
             raise SystemExit("bench.py: no CUDA device; the native arm has no CPU fallback")
         line = run_native(args, rank, world, local_rank)
     if rank == 0 and line is not None:
-        print(json.dumps(line), flush=True)
+        os.write(out_fd, (json.dumps(line) + "\n").encode())
 
 
 if __name__ == "__main__":

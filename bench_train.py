@@ -178,11 +178,16 @@ def main():
     ap.add_argument("--fused-optimizer", action="store_true",
                     help="use osudit.optim.FusedAdamWEMA instead of torch.optim.AdamW + the update_ema loop")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: keep the real stdout aside and point fd 1 at stderr, so that anything a
+    # library writes to C stdout (NCCL prints its version banner there when NCCL_DEBUG is set) cannot precede it
+    sys.stdout.flush()
+    out_fd = os.dup(1)
+    os.dup2(2, 1)
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     line = run_reference(args, rank) if args.impl == "reference" else \
         run_native(args, rank, world, int(os.environ.get("LOCAL_RANK", 0)))
     if rank == 0 and line is not None:
-        print(json.dumps(line), flush=True)
+        os.write(out_fd, (json.dumps(line) + "\n").encode())
 
 
 if __name__ == "__main__":
