@@ -197,6 +197,17 @@ int osudit_diffusion_loss(const float* model_out, const float* x0, const float* 
 int osudit_scale_rows(const float* in, const float* g, int B, int64_t per_row, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Beatmap feature builder: data_loading.py:146-151 (calc_distances), :172-187
+ * (split_and_process_sequence_no_augment), :195-203 / sample.py:64-65 (relative time), on the device.
+ * seq fp32 [B, R, T], rows = x px, y px, time ms, then R-3 one-hot type rows (R = 19 in the reference).
+ * o [B, T] = time - time[0] (+ o_shift[b] when o_shift != NULL: the random offset of training windows);
+ * c [B, 128 + R - 3, T] = [cos | sin](dist * freqs64) over the distance to the previous object (the first one
+ * measured from the playfield centre), then the type rows; x [B, 2, T] = pos / (512, 384), or NULL to skip it.
+ * ---------------------------------------------------------------------------------------------- */
+int osudit_beatmap_features(const float* seq, int B, int R, int T, const float* freqs64, const float* o_shift,
+                            float* x, float* o, float* c, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Optimizer step: one multi-tensor launch for AdamW + EMA + gradient unscale + skip on
  * non-finite gradients.  Opt-in replacement of `scaler.step(opt)` with torch.optim.AdamW (train.py:154,
  * 258-259) followed by `update_ema(ema, model.module)` (train.py:36-45,261).

@@ -247,3 +247,54 @@ def test_cuda_graph_step_equals_eager(monkeypatch, use_cfg):
     assert torch.equal(eager2[0], replay2[0])
     assert not torch.equal(eager2[1], eager[1])
     graphs._cache.clear()
+
+
+@torch.no_grad()
+def test_refine_loop_with_second_checkpoint_and_inpaint_callback():
+    """SURVEY §8(f)3 — sample.py:151-172: after the sampling loop, `refine_iters` more p_sample calls at t = 0 with
+    a second (refine) checkpoint; test_toy.py:56-69: an in-paint `denoised_fn` that pins known coordinates.  Both go
+    through the drop-in API (the graph-replayed step for the former, the two-phase step kernel for the latter)."""
+    from diffusion import create_diffusion
+    from osudit import graphs
+    shape, sd1, m1 = build("DiT-S", seed=1)
+    _, sd2, m2 = build("DiT-S", seed=2)
+    T = 256
+    z, o, c, y = synth.sampling_batch(1, T, seed=6)
+    mask = synth.band_mask(T, 128)
+    od, cd, yd, maskd = to_dev(o, c, y, mask)
+    kw = dict(o=od, c=cd, y=yd, cfg_scale=1.5, attn_mask=maskd)
+    s = odiff.Schedule("100")
+    d = create_diffusion("100", noise_schedule="squaredcos_cap_v2")
+    graphs._cache.clear()
+    t0 = torch.zeros(2, dtype=torch.long)
+    x = torch.rand(2, 2, T, generator=torch.Generator().manual_seed(3))  # a "sampled" map in playfield units
+    x[1] = x[0]
+    xd = x.to(DEV)
+    for it, (m, sd) in enumerate(((m1, sd1), (m2, sd2), (m2, sd2), (m2, sd2))):  # last model step, then 3 refine steps
+        ref_out = odit.forward_with_cfg(sd, shape.heads, x, odiff.original_timesteps(s, t0), o, c, y, 1.5, mask)
+        ref = odiff.p_sample(s, ref_out, x, t0, torch.zeros_like(x))  # no noise is added at t = 0
+        got = d.p_sample(m.forward_with_cfg, xd, t0.to(DEV), model_kwargs=kw)
+        assert float((got["sample"].cpu() - ref["sample"]).abs().max()) < 2e-3, it
+        assert torch.equal(got["sample"], got["pred_xstart"])  # posterior mean at t = 0 is the clamped x0
+        x, xd = ref["sample"], ref["sample"].to(DEV)  # teacher-forced
+    assert len(graphs._cache) == 2  # one captured step per checkpoint, the refine iterations replay the second
+    # in-paint: keep the first 100 datapoints fixed
+    keep = torch.zeros(2, 2, T, dtype=torch.bool)
+    keep[:, :, :100] = True
+    target = torch.rand(2, 2, T, generator=torch.Generator().manual_seed(4))
+    t = torch.full((2,), 30)
+    noise = torch.randn(2, 2, T, generator=torch.Generator().manual_seed(5))
+    ref_out = odit.forward_with_cfg(sd1, shape.heads, x, odiff.original_timesteps(s, t), o, c, y, 1.5, mask)
+    ref = odiff.p_sample(s, ref_out, x, t, noise, denoised_fn=lambda x0: torch.where(keep, target, x0))
+    import diffusion.gaussian_diffusion as gd
+    real = gd.th.randn_like
+    gd.th.randn_like = lambda v: noise.to(v.device)
+    try:
+        keepd, targetd = keep.to(DEV), target.to(DEV)
+        got = d.p_sample(m1.forward_with_cfg, x.to(DEV), t.to(DEV), model_kwargs=kw,
+                         denoised_fn=lambda x0: torch.where(keepd, targetd, x0))
+    finally:
+        gd.th.randn_like = real
+    assert torch.equal(got["pred_xstart"][:, :, :100].cpu(), target[:, :, :100].clamp(-1, 2))
+    assert float((got["sample"].cpu() - ref["sample"])[:, :, :100].abs().max()) < 1e-5  # exact where pinned
+    graphs._cache.clear()

@@ -169,3 +169,18 @@ def test_eager_library_restatement_matches_oracle():
     a = eager_cuda.forward_with_cfg(sd, shape.heads, z, t, o, c, y, 1.5, mask)
     b = odit.forward_with_cfg(sd, shape.heads, z, t, o, c, y, 1.5, mask)
     assert _rel(a, b) < 1e-5
+
+
+def test_feature_builder_oracle_matches_reference_golden(golden_dir):
+    """oracle/features.py against data_loading.py's own outputs (tests/golden/make_golden_features.py): bit-exact."""
+    from oracle import features as ofeat
+    g = _load(golden_dir, "features.npz")
+    x, o, c = ofeat.beatmap_features(g["seq"])
+    assert torch.equal(x, g["x"]) and torch.equal(o, g["o_sampling"]) and torch.equal(c, g["c"])
+    assert torch.equal(ofeat.calc_distances(g["seq"].clone()), g["dist"])
+    s, e = [int(v) for v in g["win"]]
+    _, ow, _ = ofeat.beatmap_features(g["seq"][:, s:e], float(g["shift"]))
+    assert torch.equal(ow, g["ow"])
+    # synthetic inputs used by the benches are built the same way
+    xs, os_, cs = synth.beatmap_features(64, seed=5)
+    assert cs.shape == (144, 64) and float(os_[0]) == 0.0 and float(xs.max()) <= 1.0
