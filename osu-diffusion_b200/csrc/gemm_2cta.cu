@@ -29,13 +29,22 @@ namespace g2 {
 constexpr int BM = 128;        // rows per CTA (256 per pair)
 constexpr int BN = 256;        // columns per pair; each CTA stages BN/2 rows of B
 constexpr int BK = 64;
-constexpr int kStages = 6;
+#ifndef OSUDIT_G2_EPI_GROUPS
+#define OSUDIT_G2_EPI_GROUPS 1
+#endif
+// Epilogue warp groups: each group is 8 warps (2 per TMEM lane quadrant) that own every kEpiGroups-th 64-column
+// chunk of a tile, with their own staging buffers, named barrier and TMA-store bookkeeping.  Measured on B200
+// (tools/gemm_bench.py, M = 262144): two groups (16 epilogue warps, 5 instead of 6 operand stages) give fc1+GELU
+// +2 % (1202 -> 1226 TFLOP/s) but QKV -4 %, out-proj -4 %, fc2 -2 %: the GELU epilogue is not latency-bound, so
+// the default stays one group.
+constexpr int kEpiGroups = OSUDIT_G2_EPI_GROUPS;
+constexpr int kStages = kEpiGroups == 1 ? 6 : 5;
 constexpr int kBytesA = BM * BK * 2;
 constexpr int kBytesB = (BN / 2) * BK * 2;
 constexpr int kStageBytes = kBytesA + kBytesB;  // 32 KB per CTA
 constexpr int kStagingBytes = BM * 128;
-constexpr int kThreads = 64 + 256;
-constexpr int kSmemBytes = kStages * kStageBytes + 2 * kStagingBytes + 1024;
+constexpr int kThreads = 64 + 256 * kEpiGroups;
+constexpr int kSmemBytes = kStages * kStageBytes + 2 * kEpiGroups * kStagingBytes + 1024;
 
 struct Params {
   CUtensorMap tma_a, tma_b, tma_out;
@@ -103,7 +112,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm2_kernel(const __grid_constant__ Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* staging = smem + kStages * kStageBytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + 2 * kStagingBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + 2 * kEpiGroups * kStagingBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full = empty_bar + kStages;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -125,7 +134,7 @@ gemm2_kernel(const __grid_constant__ Params p) {
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);    // per CTA: one multicast commit
-      mbar_init(&tmem_empty[i], 16);  // leader's: 8 epilogue warps of each CTA
+      mbar_init(&tmem_empty[i], 16 * kEpiGroups);  // leader's: every epilogue warp of both CTAs
     }
     fence_mbar_init();
   }
@@ -191,9 +200,11 @@ gemm2_kernel(const __grid_constant__ Params p) {
   } else {
     // ---------------------------------------------------------------- epilogue (both CTAs)
     constexpr int kChunks = BN / 64;
-    const int ep_tid = threadIdx.x - 64;
+    const int grp = (warp - 2) >> 3;                 // epilogue warp group
+    const int ep_tid = (threadIdx.x - 64) & 255;     // thread index within the group
     const int quad = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int half = ((warp - 2) >> 2) & 1;
+    uint8_t* const my_staging = staging + grp * 2 * kStagingBytes;
     const int row = quad * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -205,16 +216,16 @@ gemm2_kernel(const __grid_constant__ Params p) {
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN);
 #pragma unroll 1
-      for (int c = 0; c < kChunks; ++c, ++chunk_ctr) {
-        uint8_t* buf = staging + (chunk_ctr & 1) * kStagingBytes;
+      for (int c = grp; c < kChunks; c += kEpiGroups, ++chunk_ctr) {
+        uint8_t* buf = my_staging + (chunk_ctr & 1) * kStagingBytes;
         if (ep_tid == 0) tma_store_wait_read<1>();
-        named_bar_sync(1, 256);
+        named_bar_sync(1 + grp, 256);
         const int ncol0 = n0 + c * 64;
         uint8_t* my_row = buf + row * 128;
         uint32_t r[32];
         tmem_ld_32x32(t_row + static_cast<uint32_t>(c * 64 + half * 32), r);
         tmem_ld_wait();
-        if (c == kChunks - 1) {  // accumulator fully read: hand the stage back to the leader's MMA warp
+        if (c + kEpiGroups >= kChunks) {  // this warp's last read of the accumulator: hand the stage back
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(mapa_rank0(smem_u32(&tmem_empty[acc])));
@@ -245,7 +256,7 @@ gemm2_kernel(const __grid_constant__ Params p) {
           *reinterpret_cast<uint4*>(my_row + ((jj ^ (row & 7)) << 4)) = o;
         }
         fence_proxy_async_smem();
-        named_bar_sync(1, 256);
+        named_bar_sync(1 + grp, 256);
         if (ep_tid == 0) {
           tma_store_2d(&p.tma_out, buf, ncol0, m0);
           tma_store_commit();
