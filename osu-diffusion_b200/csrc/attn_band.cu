@@ -263,33 +263,11 @@ static int launch_band(const void* qkv, void* out, int B, int T, int H, int wl, 
 // =================================================================================== backward
 // Flash-style backward of the same attention (autograd of nn.MultiheadAttention's core in the
 // reference, train.py:257).  P is recomputed from Q, K and the forward's log2-domain LSE:
-//   P = exp2(S * scale_log2 - lse),  delta = rowsum(dO * O),  dS = P * (dP - delta),
+//   P = exp2(S * scale_log2 - lse),  delta = rowsum(dO * O) (computed by the dQ kernel),  dS = P * (dP - delta),
 //   dQ = scale * dS K,  dK = scale * dS^T Q,  dV = P^T dO,  with dP = dO V^T.
 // Two kernels so that no atomics are needed: one owns 64 queries (dQ), one owns 64 keys (dK, dV).
 // head_dim 64 and 72 (DiT-XL) share the code through Geo<HD>: for 72 the contraction over the head
 // dimension runs 5 k-steps with a zero padding chunk and the 10th output block is dropped.
-
-// delta[b, h, t] = sum_d dO[b, t, h, d] * O[b, t, h, d]
-__global__ void __launch_bounds__(256)
-attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout,
-                  float* __restrict__ delta, int64_t rows, int T, int H, int HD) {
-  const int lane = threadIdx.x & 31;
-  const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  const int64_t b = row / T, t = row - b * T;
-  for (int h = 0; h < H; ++h) {
-    float v = 0.f;
-    for (int c = lane * 2; c < HD; c += 64) {
-      const int64_t off = (row * H + h) * HD + c;
-      const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(o + off));
-      const float2 d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dout + off));
-      v = fmaf(a.x, d.x, fmaf(a.y, d.y, v));
-    }
-#pragma unroll
-    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
-    if (lane == 0) delta[(b * H + h) * T + t] = v;
-  }
-}
 
 // Column sums over the CTA's 64 rows of a [64 x HD] accumulator tile held as mma fragments (rows lane/4 and
 // lane/4 + 8 of each warp's 16, columns db*8 + (lane&3)*2 + {0,1}), added to dst[0..HD).  Must be called
@@ -319,8 +297,8 @@ __device__ __forceinline__ void tile_colsum(const float (&acc)[Geo<HD>::kDBlocks
 
 template <int HD>
 __global__ void __launch_bounds__(128)
-attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout,
-                   const float* __restrict__ lse, const float* __restrict__ delta,
+attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ out_fwd,
+                   const __nv_bfloat16* __restrict__ dout, const float* __restrict__ lse, float* __restrict__ delta,
                    __nv_bfloat16* __restrict__ dqkv, int T, int H, int wl, int wr, float scale_log2,
                    float scale, float* __restrict__ dbias) {
   using G = Geo<HD>;
@@ -362,7 +340,27 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
     const bool ok = qrow[rr] < T;
     const int64_t idx = (static_cast<int64_t>(b) * H + h) * T + (ok ? qrow[rr] : 0);
     row_lse[rr] = ok ? lse[idx] : 0.f;
-    row_delta[rr] = ok ? delta[idx] : 0.f;
+  }
+  {  // delta = rowsum(dO * O) of this warp's 16 query rows (lane -> row lane/2, half lane&1), published for the
+     // dK/dV kernel that runs next and handed to the two fragment rows this lane owns
+    const int r = q0 + warp * 16 + (lane >> 1);
+    float acc = 0.f;
+    if (r < T) {
+      const __nv_bfloat162* po = reinterpret_cast<const __nv_bfloat162*>(
+          out_fwd + (static_cast<int64_t>(b) * T + r) * D + h * HD) + (lane & 1) * (HD / 4);
+      const __nv_bfloat162* pd = reinterpret_cast<const __nv_bfloat162*>(gdo + static_cast<int64_t>(r) * D) +
+                                 (lane & 1) * (HD / 4);
+#pragma unroll
+      for (int i = 0; i < HD / 4; ++i) {
+        const float2 a = __bfloat1622float2(po[i]);
+        const float2 d = __bfloat1622float2(pd[i]);
+        acc = fmaf(a.x, d.x, fmaf(a.y, d.y, acc));
+      }
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    if ((lane & 1) == 0 && r < T) delta[(static_cast<int64_t>(b) * H + h) * T + r] = acc;
+    row_delta[0] = __shfl_sync(0xffffffffu, acc, 2 * (lane >> 2));
+    row_delta[1] = __shfl_sync(0xffffffffu, acc, 2 * (lane >> 2) + 16);
   }
 
   for (int kt = kt_lo; kt <= kt_hi; ++kt) {
@@ -637,7 +635,7 @@ extern "C" int osudit_attn_band(const void* qkv, void* out, int B, int T, int H,
 }
 
 template <int HD>
-static int launch_bwd(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv, int B,
+static int launch_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, void* dqkv, int B,
                       int T, int H, int w_left, int w_right, float* dbias, cudaStream_t st) {
   constexpr int smem_dq = 6 * Geo<HD>::kTileBytes;
   constexpr int smem_dkv = 6 * Geo<HD>::kTileBytes + 4 * kBQ * sizeof(float);
@@ -654,7 +652,8 @@ static int launch_bwd(const void* qkv, const void* dout, const float* lse, const
   const float scale_log2 = 1.4426950408889634f * scale;
   dim3 grid((T + kBQ - 1) / kBQ, H, B);
   attn_bwd_dq_kernel<HD><<<grid, 128, smem_dq, st>>>(
-      static_cast<const __nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(dout), lse, delta,
+      static_cast<const __nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(out),
+      static_cast<const __nv_bfloat16*>(dout), lse, delta,
       static_cast<__nv_bfloat16*>(dqkv), T, H, w_left, w_right, scale_log2, scale, dbias);
   OSUDIT_CHECK_LAUNCH();
   attn_bwd_dkv_kernel<HD><<<grid, 128, smem_dkv, st>>>(
@@ -673,11 +672,7 @@ extern "C" int osudit_attn_band_bwd(const void* qkv, const void* out, const void
   if (w_left < 0 || w_left > T) w_left = T;
   if (w_right < 0 || w_right > T) w_right = T;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int64_t rows = static_cast<int64_t>(B) * T;
-  attn_delta_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, st>>>(
-      static_cast<const __nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(dout), delta, rows, T, H,
-      head_dim);
-  OSUDIT_CHECK_LAUNCH();
-  if (head_dim == 64) return launch_bwd<64>(qkv, dout, lse, delta, dqkv, B, T, H, w_left, w_right, dbias_qkv, st);
-  return launch_bwd<72>(qkv, dout, lse, delta, dqkv, B, T, H, w_left, w_right, dbias_qkv, st);
+  if (head_dim == 64)
+    return launch_bwd<64>(qkv, out, dout, lse, delta, dqkv, B, T, H, w_left, w_right, dbias_qkv, st);
+  return launch_bwd<72>(qkv, out, dout, lse, delta, dqkv, B, T, H, w_left, w_right, dbias_qkv, st);
 }
