@@ -85,6 +85,17 @@ int osudit_transpose_bf16(const void* in, void* out, int64_t rows, int64_t cols,
 /* backward == 0: out = gelu_tanh(pre);  backward == 1: out = dy * gelu_tanh'(pre).  bf16, n % 8 == 0. */
 int osudit_gelu(const void* pre, const void* dy, void* out, int64_t n, int backward, void* stream);
 
+/* Single-segment bf16 GEMM (as osudit_gemm_bf16) whose epilogue also touches a second bf16 [M, N] tensor `aux`:
+ *   OSUDIT_EPI_BF16_GELU_SAVE: aux = A B^T + bias (the fc1 pre-activation, kept for the backward),
+ *                              out = gelu_tanh(A B^T + bias)                   (training forward, models.py:112-119)
+ *   OSUDIT_EPI_BF16_DGELU:     out = (A B^T) * gelu_tanh'(aux)                 (the gradient through that GELU)
+ * Fused into the CTA-pair kernel's epilogue where that kernel applies; two launches with the same result otherwise. */
+#define OSUDIT_EPI_BF16_GELU_SAVE 3
+#define OSUDIT_EPI_BF16_DGELU 4
+int osudit_gemm_bf16_aux(const void* a, int64_t lda, const void* b, int64_t ldb, int64_t K, int64_t M, int64_t N,
+                         const float* bias, int epilogue, void* out, int64_t ldo, void* aux, int64_t ld_aux,
+                         void* stream);
+
 /* out[rows, N] = dy * gelu_tanh'(pre) and dbias[N] (fp32, ACCUMULATED, may be NULL) += column sums of out:
  * the fc1 pre-activation gradient together with the fc1 bias gradient.  bf16, N % 8 == 0. */
 int osudit_gelu_bwd(const void* pre, const void* dy, void* out, int64_t rows, int N, float* dbias, void* stream);

@@ -47,12 +47,18 @@ constexpr int kThreads = 64 + 256 * kEpiGroups;
 constexpr int kSmemBytes = kStages * kStageBytes + 2 * kEpiGroups * kStagingBytes + 1024;
 
 struct Params {
-  CUtensorMap tma_a, tma_b, tma_out;
+  CUtensorMap tma_a, tma_b, tma_out, tma_aux;
   int kblocks, M, N, m_tiles, n_tiles;
   const float* bias;
+  const __nv_bfloat16* aux;  // EPI_BF16_DGELU: the saved pre-activation, read straight from global memory
+  int64_t ld_aux;
 };
 
-enum : int { EPI_BF16 = 1, EPI_BF16_GELU = 2 };
+// EPI_BF16_GELU_SAVE (training forward of fc1): aux = acc + bias (the pre-activation the backward needs),
+// out = gelu(acc + bias) — two stores per chunk instead of a separate GELU pass over HBM.
+// EPI_BF16_DGELU (training backward through the GELU): out = acc * gelu'(aux), the data gradient of fc2
+// multiplied by the activation derivative in the epilogue, so du is never materialised.
+enum : int { EPI_BF16 = 1, EPI_BF16_GELU = 2, EPI_BF16_GELU_SAVE = 3, EPI_BF16_DGELU = 4 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -105,6 +111,16 @@ __device__ __forceinline__ float gelu_tanh(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
   const float hx = 0.5f * x;
   return fmaf(hx, t, hx);
+}
+
+__device__ __forceinline__ float gelu_tanh_grad(float x) {
+  const float x2 = x * x;
+  const float u = x * fmaf(x2, 0.044715f * 0.7978845608028654f, 0.7978845608028654f);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+  const float du = fmaf(x2, 3.0f * 0.044715f * 0.7978845608028654f, 0.7978845608028654f);
+  const float hx = 0.5f * x;
+  return fmaf(hx * du, fmaf(-t, t, 1.0f), fmaf(0.5f, t, 0.5f));
 }
 
 template <int EPI>
@@ -216,12 +232,16 @@ gemm2_kernel(const __grid_constant__ Params p) {
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN);
 #pragma unroll 1
-      for (int c = grp; c < kChunks; c += kEpiGroups, ++chunk_ctr) {
-        uint8_t* buf = my_staging + (chunk_ctr & 1) * kStagingBytes;
-        if (ep_tid == 0) tma_store_wait_read<1>();
-        named_bar_sync(1 + grp, 256);
+      for (int c = grp; c < kChunks; c += kEpiGroups) {
         const int ncol0 = n0 + c * 64;
-        uint8_t* my_row = buf + row * 128;
+        uint4 ax[4];
+        if (EPI == EPI_BF16_DGELU) {  // this thread's 32 pre-activations (64 B of its row), in flight before the TMEM wait
+          const bool in = m0 + row < p.M;
+          const uint4* ap = reinterpret_cast<const uint4*>(p.aux + static_cast<int64_t>(in ? m0 + row : 0) * p.ld_aux +
+                                                           ncol0 + half * 32);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) ax[j] = in ? __ldg(ap + j) : make_uint4(0u, 0u, 0u, 0u);
+        }
         uint32_t r[32];
         tmem_ld_32x32(t_row + static_cast<uint32_t>(c * 64 + half * 32), r);
         tmem_ld_wait();
@@ -241,25 +261,45 @@ gemm2_kernel(const __grid_constant__ Params p) {
           v[i + 2] = __uint_as_float(r[i + 2]) + b.z;
           v[i + 3] = __uint_as_float(r[i + 3]) + b.w;
         }
-        if (EPI == EPI_BF16_GELU) {
+        if (EPI == EPI_BF16_DGELU) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = gelu_tanh(v[i]);
-        }
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t* w = reinterpret_cast<const uint32_t*>(&ax[j]);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint4 o;
-          o.x = pack_bf16(v[8 * j + 0], v[8 * j + 1]);
-          o.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
-          o.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
-          o.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
-          const int jj = half * 4 + j;
-          *reinterpret_cast<uint4*>(my_row + ((jj ^ (row & 7)) << 4)) = o;
+            for (int k = 0; k < 4; ++k) {
+              const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[k]));
+              v[8 * j + 2 * k] *= gelu_tanh_grad(x.x);
+              v[8 * j + 2 * k + 1] *= gelu_tanh_grad(x.y);
+            }
+          }
         }
-        fence_proxy_async_smem();
-        named_bar_sync(1 + grp, 256);
-        if (ep_tid == 0) {
-          tma_store_2d(&p.tma_out, buf, ncol0, m0);
-          tma_store_commit();
+        constexpr int kPasses = EPI == EPI_BF16_GELU_SAVE ? 2 : 1;  // SAVE: the pre-activation first, then its GELU
+#pragma unroll
+        for (int pass = 0; pass < kPasses; ++pass, ++chunk_ctr) {
+          uint8_t* buf = my_staging + (chunk_ctr & 1) * kStagingBytes;
+          if (ep_tid == 0) tma_store_wait_read<1>();
+          named_bar_sync(1 + grp, 256);
+          uint8_t* my_row = buf + row * 128;
+          if (EPI == EPI_BF16_GELU || (EPI == EPI_BF16_GELU_SAVE && pass == 1)) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = gelu_tanh(v[i]);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 o;
+            o.x = pack_bf16(v[8 * j + 0], v[8 * j + 1]);
+            o.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+            o.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
+            o.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+            const int jj = half * 4 + j;
+            *reinterpret_cast<uint4*>(my_row + ((jj ^ (row & 7)) << 4)) = o;
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(1 + grp, 256);
+          if (ep_tid == 0) {
+            tma_store_2d((EPI == EPI_BF16_GELU_SAVE && pass == 0) ? &p.tma_aux : &p.tma_out, buf, ncol0, m0);
+            tma_store_commit();
+          }
         }
       }
       acc ^= 1;
@@ -296,12 +336,13 @@ static int launch2(const Params& p, cudaStream_t stream) {
 }  // namespace g2
 
 bool gemm_2cta_applicable(int nseg, int64_t M, int64_t N, int epilogue) {
-  return nseg == 1 && (epilogue == g2::EPI_BF16 || epilogue == g2::EPI_BF16_GELU) && N % 256 == 0 &&
+  return nseg == 1 && epilogue >= g2::EPI_BF16 && epilogue <= g2::EPI_BF16_DGELU && N % 256 == 0 &&
          M >= 256 * 37;  // at least half a wave of 256-row tiles, otherwise the 1-CTA kernel balances better
 }
 
 int gemm_2cta_launch(const void* a, int64_t lda, const void* b, int64_t ldb, int64_t K, int64_t M, int64_t N,
-                     const float* bias, int epilogue, void* out, int64_t ldo, cudaStream_t stream) {
+                     const float* bias, int epilogue, void* out, int64_t ldo, void* aux, int64_t ld_aux,
+                     cudaStream_t stream) {
   using namespace g2;
   Params p;
   p.kblocks = static_cast<int>((K + BK - 1) / BK);
@@ -316,7 +357,22 @@ int gemm_2cta_launch(const void* a, int64_t lda, const void* b, int64_t ldb, int
   if (rc) return rc;
   rc = make_tensor_map_2d(&p.tma_out, out, N, M, ldo * 2, 64, BM, false);
   if (rc) return rc;
-  return epilogue == EPI_BF16 ? launch2<EPI_BF16>(p, stream) : launch2<EPI_BF16_GELU>(p, stream);
+  p.aux = static_cast<const __nv_bfloat16*>(aux);
+  p.ld_aux = ld_aux;
+  p.tma_aux = p.tma_out;
+  if (epilogue == EPI_BF16_GELU_SAVE || epilogue == EPI_BF16_DGELU) {
+    if (aux == nullptr || (ld_aux % 8) != 0) return set_error(-1, "gemm: aux must be given with ld_aux % 8 == 0");
+    if (epilogue == EPI_BF16_GELU_SAVE) {
+      rc = make_tensor_map_2d(&p.tma_aux, aux, N, M, ld_aux * 2, 64, BM, false);
+      if (rc) return rc;
+    }
+  }
+  switch (epilogue) {
+    case EPI_BF16: return launch2<EPI_BF16>(p, stream);
+    case EPI_BF16_GELU: return launch2<EPI_BF16_GELU>(p, stream);
+    case EPI_BF16_GELU_SAVE: return launch2<EPI_BF16_GELU_SAVE>(p, stream);
+    default: return launch2<EPI_BF16_DGELU>(p, stream);
+  }
 }
 
 }  // namespace osudit

@@ -426,7 +426,8 @@ int make_tensor_map_2d(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t 
 
 bool gemm_2cta_applicable(int nseg, int64_t M, int64_t N, int epilogue);
 int gemm_2cta_launch(const void* a, int64_t lda, const void* b, int64_t ldb, int64_t K, int64_t M, int64_t N,
-                     const float* bias, int epilogue, void* out, int64_t ldo, cudaStream_t stream);
+                     const float* bias, int epilogue, void* out, int64_t ldo, void* aux, int64_t ld_aux,
+                     cudaStream_t stream);
 
 int make_tensor_map_3d(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2,
                        uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t b0, uint32_t b1) {
@@ -470,7 +471,7 @@ static int gemm_entry(int nseg, const void* const* a, const int64_t* lda, const 
     }();
     if (use_pair && kb_per_split == 0 && gemm_2cta_applicable(nseg, M, N, epilogue)) {
       if (k[0] <= 0 || (k[0] % 8) != 0) return set_error(-1, "gemm: K must be a positive multiple of 8");
-      return gemm_2cta_launch(a[0], lda[0], b[0], ldb[0], k[0], M, N, bias, epilogue, out, ldo,
+      return gemm_2cta_launch(a[0], lda[0], b[0], ldb[0], k[0], M, N, bias, epilogue, out, ldo, nullptr, 0,
                               static_cast<cudaStream_t>(stream));
     }
   }
@@ -522,6 +523,38 @@ extern "C" int osudit_gemm_bf16(int nseg, const void* const* a, const int64_t* l
                                 int64_t M, int64_t N, const float* bias, int epilogue, void* out,
                                 int64_t ldo, void* stream) {
   return gemm_entry(nseg, a, lda, b, ldb, k, M, N, bias, epilogue, out, ldo, stream, 0);
+}
+
+extern "C" int osudit_gelu(const void* pre, const void* dy, void* out, int64_t n, int backward, void* stream);
+extern "C" int osudit_gelu_bwd(const void* pre, const void* dy, void* out, int64_t rows, int N, float* dbias,
+                               void* stream);
+
+extern "C" int osudit_gemm_bf16_aux(const void* a, int64_t lda, const void* b, int64_t ldb, int64_t K, int64_t M,
+                                    int64_t N, const float* bias, int epilogue, void* out, int64_t ldo, void* aux,
+                                    int64_t ld_aux, void* stream) {
+  if (epilogue != 3 && epilogue != 4) return set_error(-1, "gemm_aux: epilogue must be GELU_SAVE (3) or DGELU (4)");
+  if (aux == nullptr || out == nullptr) return set_error(-1, "gemm_aux: out and aux are required");
+  if (M <= 0 || N <= 0 || K <= 0 || (K % 8) || (N % 8)) return set_error(-1, "gemm_aux: bad shape");
+  static const bool use_pair = [] {
+    const char* e = getenv("OSUDIT_GEMM_2CTA");
+    return !(e && e[0] == '0');
+  }();
+  if (use_pair && gemm_2cta_applicable(1, M, N, epilogue))
+    return gemm_2cta_launch(a, lda, b, ldb, K, M, N, bias, epilogue, out, ldo, aux, ld_aux,
+                            static_cast<cudaStream_t>(stream));
+  // shapes the CTA-pair kernel does not take: the same result in two launches
+  if (ldo != N || ld_aux != N) return set_error(-1, "gemm_aux: the two-launch path needs contiguous out / aux");
+  const void* as[1] = {a};
+  const void* bs[1] = {b};
+  const int64_t ldas[1] = {lda}, ldbs[1] = {ldb}, ks[1] = {K};
+  if (epilogue == 3) {
+    int rc = gemm_entry(1, as, ldas, bs, ldbs, ks, M, N, bias, EPI_BF16, aux, ld_aux, stream, 0);
+    if (rc) return rc;
+    return osudit_gelu(aux, nullptr, out, M * N, 0, stream);
+  }
+  int rc = gemm_entry(1, as, ldas, bs, ldbs, ks, M, N, bias, EPI_BF16, out, ldo, stream, 0);
+  if (rc) return rc;
+  return osudit_gelu_bwd(aux, out, out, M, static_cast<int>(N), nullptr, stream);
 }
 
 extern "C" int osudit_gemm_bf16_splitk(int nseg, const void* const* a, const int64_t* lda,

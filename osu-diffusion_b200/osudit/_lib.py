@@ -45,6 +45,7 @@ SIGNATURES = {
     "osudit_diffusion_step": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _I, _I, _P, _P, _P, _P, _P],
     "osudit_cfg_combine": [_P, _I, _I, _F, _P, _P],
     "osudit_q_sample": [_P, _P, _P, _P, _P, _I, _L, _P, _P],
+    "osudit_gemm_bf16_aux": [_P, _L, _P, _L, _L, _L, _L, _P, _I, _P, _L, _P, _L, _P],
     "osudit_beatmap_features": [_P, _I, _I, _I, _P, _P, _P, _P, _P, _P],
     "osudit_opt_chunk_elems": [],
     "osudit_adamw_ema_step": [_P, _P, _I, _F, _F, _F, _F, _F, _F, _P, _P, _P, _P],

@@ -55,6 +55,25 @@ def gemm(a_segs, b_segs, bias, epilogue: int, out: torch.Tensor) -> torch.Tensor
     return out
 
 
+EPI_BF16_GELU_SAVE, EPI_BF16_DGELU = 3, 4
+
+
+def gemm_aux(a, w, bias, epilogue: int, out, aux):
+    """Single-segment bf16 GEMM out = f(a @ w.T + bias) with a second [M, N] bf16 tensor in the epilogue:
+    GELU_SAVE writes the pre-activation to `aux` and its GELU to `out`; DGELU multiplies by gelu'(aux)."""
+    M, N = out.shape
+    if a.shape[0] != M or w.shape[0] != N or a.shape[1] != w.shape[1] or tuple(aux.shape) != (M, N):
+        raise _lib.OsuditError(f"gemm_aux: shape mismatch {tuple(a.shape)} x {tuple(w.shape)} -> {tuple(out.shape)}")
+    lib = _lib.load()
+    _lib.check(lib.osudit_gemm_bf16_aux(_chk(a, torch.bfloat16, "gemm_aux.a"), a.stride(0),
+                                        _chk(w, torch.bfloat16, "gemm_aux.w"), w.stride(0), a.shape[1], M, N,
+                                        _chk(bias, torch.float32, "gemm_aux.bias") if bias is not None else None,
+                                        epilogue, _chk(out, torch.bfloat16, "gemm_aux.out"), out.stride(0),
+                                        _chk(aux, torch.bfloat16, "gemm_aux.aux"), aux.stride(0), _stream()),
+               "osudit_gemm_bf16_aux")
+    return out
+
+
 ATTN_AUTO, ATTN_MMA_SYNC, ATTN_TCGEN05 = 0, 1, 2
 
 

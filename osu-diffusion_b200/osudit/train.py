@@ -134,8 +134,7 @@ def forward_train(model, tw: TrainWeights, x, t, o, c, y, attn_mask):
         h2 = _e(rows, D, device=dev)
         ops.ln_modulate(xa, y1, mod, base + 2 * D, base + 3 * D, base + 4 * D, T, h2, x_out=xb)
         pre = _e(rows, bw["fc1_w"].shape[0], device=dev)
-        ops.gemm([h2], [bw["fc1_w"]], f32(blk.mlp.fc1.bias), ops.EPI_BF16, pre)
-        u = ops.gelu(pre, torch.empty_like(pre))
+        u = ops.gemm_aux(h2, bw["fc1_w"], f32(blk.mlp.fc1.bias), ops.EPI_BF16_GELU_SAVE, torch.empty_like(pre), pre)
         y2 = _e(rows, D, device=dev)
         ops.gemm([u], [bw["fc2_w"]], f32(blk.mlp.fc2.bias), ops.EPI_BF16, y2)
         saved_blocks.append(dict(xa=xa, h1=h1, qkv=qkv, att=att, lse=lse, y1=y1, xb=xb, h2=h2, pre=pre, u=u, y2=y2))
@@ -192,9 +191,9 @@ def backward_train(model, tw: TrainWeights, S, dout):
         hidden = sv["pre"].shape[1]
         # ---- MLP branch: x_out = xb + gate_mlp * y2 (dy2 = gate_mlp * dx is already in dy_buf)
         grads[blk.mlp.fc2.weight] = _wgrad(dy2, sv["u"], dev)
-        du = ops.gemm([dy2], [bw["fc2_wt"]], None, ops.EPI_BF16, _e(rows, hidden, device=dev))
-        grads[blk.mlp.fc1.bias] = z32(hidden)
-        dpre = ops.gelu_bwd(sv["pre"], du, du, dbias=grads[blk.mlp.fc1.bias])  # in place over du
+        # d pre = (dy2 W2) * gelu'(pre): the GELU derivative is applied in the data-gradient GEMM's epilogue
+        dpre = ops.gemm_aux(dy2, bw["fc2_wt"], None, ops.EPI_BF16_DGELU, _e(rows, hidden, device=dev), sv["pre"])
+        grads[blk.mlp.fc1.bias] = ops.colsum(dpre, z32(hidden))
         grads[blk.mlp.fc1.weight] = _wgrad(dpre, sv["h2"], dev)
         dh2 = ops.gemm([dpre], [bw["fc1_wt"]], None, ops.EPI_BF16, dh_buf)
         # ---- LN2 backward into dx, then the attention branch's gate: xb = xa + gate_msa * y1

@@ -67,6 +67,25 @@ def test_gelu_forward_backward():
     assert rel(dbias - 1.0, x2.grad.sum(0)) < 2e-3
 
 
+@pytest.mark.parametrize("M", [9700, 300])  # CTA-pair kernel with the fused epilogue / two-launch path
+def test_gemm_with_gelu_save_and_dgelu_epilogues(M):
+    g = torch.Generator(device=DEV).manual_seed(M)
+    N, K = 768, 256
+    a = bf(torch.randn(M, K, device=DEV, generator=g))
+    w = bf(torch.randn(N, K, device=DEV, generator=g) / math.sqrt(K))
+    bias = torch.randn(N, device=DEV, generator=g)
+    pre_ref = a.float() @ w.float().t() + bias
+    pre, u = torch.empty(M, N, device=DEV, dtype=torch.bfloat16), torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    ops.gemm_aux(a, w, bias, ops.EPI_BF16_GELU_SAVE, u, pre)
+    assert rel(pre.float(), pre_ref) < 3e-3
+    assert rel(u.float(), torch.nn.functional.gelu(pre_ref, approximate="tanh")) < 4e-3
+    # backward through the GELU: out = (a w^T) * gelu'(pre)
+    x = pre.float().requires_grad_()
+    torch.nn.functional.gelu(x, approximate="tanh").backward(a.float() @ w.float().t())
+    out = ops.gemm_aux(a, w, None, ops.EPI_BF16_DGELU, torch.empty_like(pre), pre)
+    assert rel(out.float(), x.grad) < 4e-3
+
+
 @pytest.mark.parametrize("f32", [False, True])
 def test_colsum(f32):
     a = torch.randn(1000, 776, device=DEV)
