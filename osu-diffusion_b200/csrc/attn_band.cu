@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/osudit.h"
 #include "common.h"
@@ -634,6 +635,287 @@ extern "C" int osudit_attn_band(const void* qkv, void* out, int B, int T, int H,
   return launch_band<72>(qkv, out, B, T, H, w_left, w_right, mask, lse, st);
 }
 
+// ----------------------------------------------------------------- backward, whole sequence in one CTA
+// Training sequences are short (seq-len 128 in BASELINE configs 3): per (sample, head) the whole problem —
+// Q, K, V, dO (4 x 16 KB) and the recomputed P and dS (2 x 32 KB, bf16) — fits in shared memory, so one CTA of
+// 8 warps produces dQ, dK and dV together: S and dP are computed once (the two-kernel path computes them twice),
+// every operand is loaded once, and nothing but the results touches HBM.
+//   phase 1 (warp = 16 query rows): S = Q K^T, P = exp2(S*scale_log2 - lse), dP = dO V^T, dS = P*(dP - delta)
+//            -> P, dS to shared memory;  dQ = scale * dS K from the register fragments.
+//   phase 2 (warp = 16 key rows):  dV = P^T dO,  dK = scale * dS^T Q  (A operands = P / dS read through
+//            ldmatrix.trans, i.e. transposed on the fly).
+// head_dim 64, T <= 128; band semantics as everywhere else.
+constexpr int kSmallT = 128;
+
+__device__ __forceinline__ uint32_t off_p(int r, int ch) {  // [128][128] bf16, 256-byte rows, XOR-swizzled chunks
+  return r * 256 + ((ch ^ (r & 7)) << 4);
+}
+
+__global__ void __launch_bounds__(256, 1)
+attn_bwd_small_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ out_fwd,
+                      const __nv_bfloat16* __restrict__ dout, const float* __restrict__ lse,
+                      __nv_bfloat16* __restrict__ dqkv, int T, int H, int wl, int wr, float scale_log2, float scale,
+                      float* __restrict__ dbias) {
+  constexpr int HD = 64;
+  using G = Geo<HD>;
+  extern __shared__ __align__(128) uint8_t smem_attn[];
+  uint8_t* sQ = smem_attn;
+  uint8_t* sK = sQ + 2 * G::kTileBytes;
+  uint8_t* sV = sK + 2 * G::kTileBytes;
+  uint8_t* sdO = sV + 2 * G::kTileBytes;
+  uint8_t* sP = sdO + 2 * G::kTileBytes;
+  uint8_t* sdS = sP + kSmallT * 256;
+  float* s_col = reinterpret_cast<float*>(sdS + kSmallT * 256);  // [3][64] bias-gradient partial sums
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int D = H * HD;
+  const int64_t ld = 3 * static_cast<int64_t>(D);
+  const __nv_bfloat16* gq = qkv + static_cast<int64_t>(b) * T * ld + h * HD;
+  const __nv_bfloat16* gdo = dout + static_cast<int64_t>(b) * T * D + h * HD;
+  const __nv_bfloat16* go = out_fwd + static_cast<int64_t>(b) * T * D + h * HD;
+
+  for (int idx = tid; idx < kSmallT * G::kChunks; idx += 256) {
+    const int r = idx >> 3, ch = idx & 7;
+    const bool valid = r < T;
+    const int64_t rr = valid ? r : 0;
+    cp_async_16(sQ + G::off(r, ch), gq + rr * ld + ch * 8, valid);
+    cp_async_16(sK + G::off(r, ch), gq + rr * ld + D + ch * 8, valid);
+    cp_async_16(sV + G::off(r, ch), gq + rr * ld + 2 * D + ch * 8, valid);
+    cp_async_16(sdO + G::off(r, ch), gdo + rr * D + ch * 8, valid);
+  }
+  cp_async_commit();
+  if (tid < 192) s_col[tid] = 0.f;
+
+  // ---- per-row statistics of this warp's 16 queries (delta as in attn_bwd_dq_kernel)
+  const int q_base = warp * 16;
+  const int qrow[2] = {q_base + (lane >> 2), q_base + (lane >> 2) + 8};
+  float row_lse[2], row_delta[2];
+#pragma unroll
+  for (int rr = 0; rr < 2; ++rr)
+    row_lse[rr] = qrow[rr] < T ? lse[(static_cast<int64_t>(b) * H + h) * T + qrow[rr]] : 0.f;
+  {
+    const int r = q_base + (lane >> 1);
+    float acc = 0.f;
+    if (r < T) {
+      const __nv_bfloat162* po = reinterpret_cast<const __nv_bfloat162*>(go + static_cast<int64_t>(r) * D) + (lane & 1) * 16;
+      const __nv_bfloat162* pd = reinterpret_cast<const __nv_bfloat162*>(gdo + static_cast<int64_t>(r) * D) + (lane & 1) * 16;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float2 a = __bfloat1622float2(po[i]);
+        const float2 d = __bfloat1622float2(pd[i]);
+        acc = fmaf(a.x, d.x, fmaf(a.y, d.y, acc));
+      }
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    row_delta[0] = __shfl_sync(0xffffffffu, acc, 2 * (lane >> 2));
+    row_delta[1] = __shfl_sync(0xffffffffu, acc, 2 * (lane >> 2) + 16);
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+
+  // ---------------------------------------------------------------- phase 1
+  {
+    uint32_t qf[4][4], dof[4][4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const int r = q_base + (lane & 7) + ((lane >> 3) & 1) * 8;
+      const int ch = ks * 2 + (lane >> 4);
+      ldmatrix_x4(qf[ks], smem_u32(sQ) + G::off(r, ch));
+      ldmatrix_x4(dof[ks], smem_u32(sdO) + G::off(r, ch));
+    }
+    float dq[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
+    const uint32_t sk = smem_u32(sK), sv = smem_u32(sV);
+#pragma unroll 1
+    for (int kh = 0; kh < 2; ++kh) {  // two halves of 64 keys keep the accumulators at 64 registers
+      const int k0 = kh * 64;
+      if (k0 >= T) break;
+      float s[8][4], dp[8][4];
+#pragma unroll
+      for (int nb = 0; nb < 8; ++nb) {
+        s[nb][0] = s[nb][1] = s[nb][2] = s[nb][3] = 0.f;
+        dp[nb][0] = dp[nb][1] = dp[nb][2] = dp[nb][3] = 0.f;
+      }
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+        for (int nb = 0; nb < 8; nb += 2) {
+          uint32_t kf[4], vf[4];
+          const int r = k0 + nb * 8 + (lane & 7) + ((lane >> 4) & 1) * 8;
+          const int ch = ks * 2 + ((lane >> 3) & 1);
+          ldmatrix_x4(kf, sk + G::off(r, ch));
+          ldmatrix_x4(vf, sv + G::off(r, ch));
+          mma_bf16_16816(s[nb], qf[ks], kf[0], kf[1]);
+          mma_bf16_16816(s[nb + 1], qf[ks], kf[2], kf[3]);
+          mma_bf16_16816(dp[nb], dof[ks], vf[0], vf[1]);
+          mma_bf16_16816(dp[nb + 1], dof[ks], vf[2], vf[3]);
+        }
+      }
+#pragma unroll
+      for (int nb = 0; nb < 8; ++nb) {
+        float pv[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int q = qrow[e >> 1];
+          const int k = k0 + nb * 8 + (lane & 3) * 2 + (e & 1);
+          const bool ok = (k < T) && (q < T) && (k - q >= -wl) && (k - q <= wr);
+          const float p = ok ? exp2f(s[nb][e] * scale_log2 - row_lse[e >> 1]) : 0.f;
+          pv[e] = p;
+          s[nb][e] = p * (dp[nb][e] - row_delta[e >> 1]);  // dS
+        }
+        const int ch = (k0 >> 3) + nb;
+        const int cb = (lane & 3) * 4;
+        *reinterpret_cast<uint32_t*>(sP + off_p(qrow[0], ch) + cb) = pack_bf16(pv[0], pv[1]);
+        *reinterpret_cast<uint32_t*>(sP + off_p(qrow[1], ch) + cb) = pack_bf16(pv[2], pv[3]);
+        *reinterpret_cast<uint32_t*>(sdS + off_p(qrow[0], ch) + cb) = pack_bf16(s[nb][0], s[nb][1]);
+        *reinterpret_cast<uint32_t*>(sdS + off_p(qrow[1], ch) + cb) = pack_bf16(s[nb][2], s[nb][3]);
+      }
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {  // dQ += dS[:, 16 keys] K[16 keys, :]
+        uint32_t pf[4];
+        pf[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
+        pf[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
+        pf[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+        pf[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+        for (int db = 0; db < 8; db += 2) {
+          uint32_t kf[4];
+          const int r = k0 + kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+          const int ch = db + (lane >> 4);
+          ldmatrix_x4_trans(kf, sk + G::off(r, ch));
+          mma_bf16_16816(dq[db], pf, kf[0], kf[1]);
+          mma_bf16_16816(dq[db + 1], pf, kf[2], kf[3]);
+        }
+      }
+    }
+    if (T <= 64) {  // the second half of P / dS is read by phase 2 of short sequences: zero it
+      for (int nb = 8; nb < 16; ++nb) {
+        const int cb = (lane & 3) * 4;
+        *reinterpret_cast<uint32_t*>(sP + off_p(qrow[0], nb) + cb) = 0u;
+        *reinterpret_cast<uint32_t*>(sP + off_p(qrow[1], nb) + cb) = 0u;
+        *reinterpret_cast<uint32_t*>(sdS + off_p(qrow[0], nb) + cb) = 0u;
+        *reinterpret_cast<uint32_t*>(sdS + off_p(qrow[1], nb) + cb) = 0u;
+      }
+    }
+    __nv_bfloat16* gdq = dqkv + static_cast<int64_t>(b) * T * ld + h * HD;
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      if (qrow[rr] >= T) continue;
+#pragma unroll
+      for (int db = 0; db < 8; ++db)
+        *reinterpret_cast<uint32_t*>(gdq + static_cast<int64_t>(qrow[rr]) * ld + db * 8 + (lane & 3) * 2) =
+            pack_bf16(dq[db][2 * rr] * scale, dq[db][2 * rr + 1] * scale);
+    }
+    if (dbias != nullptr) {
+#pragma unroll
+      for (int db = 0; db < 8; ++db) {
+        float c0 = dq[db][0] + dq[db][2], c1 = dq[db][1] + dq[db][3];
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+          c0 += __shfl_xor_sync(0xffffffffu, c0, o);
+          c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+        }
+        if (lane < 4) {
+          atomicAdd(&s_col[db * 8 + lane * 2], c0 * scale);
+          atomicAdd(&s_col[db * 8 + lane * 2 + 1], c1 * scale);
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---------------------------------------------------------------- phase 2
+  {
+    const int key_base = warp * 16;
+    float dk[8][4], dv[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f;
+      dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f;
+    }
+    if (key_base < T) {
+      const uint32_t sq = smem_u32(sQ), sdo = smem_u32(sdO), sp = smem_u32(sP), sds = smem_u32(sdS);
+      const int n_q16 = (T + 15) >> 4;
+#pragma unroll 1
+      for (int kk = 0; kk < n_q16; ++kk) {  // contraction over 16 queries at a time
+        uint32_t pa[4], dsa[4];
+        // A = P^T / dS^T [16 keys x 16 queries]: 8x8 blocks of the stored [query][key] matrices, transposed on load
+        const int qr = kk * 16 + (lane & 7) + (lane >> 4) * 8;
+        const int kch = (key_base >> 3) + ((lane >> 3) & 1);
+        ldmatrix_x4_trans(pa, sp + off_p(qr, kch));
+        ldmatrix_x4_trans(dsa, sds + off_p(qr, kch));
+#pragma unroll
+        for (int db = 0; db < 8; db += 2) {
+          uint32_t dofr[4], qfr[4];
+          const int r = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+          const int ch = db + (lane >> 4);
+          ldmatrix_x4_trans(dofr, sdo + G::off(r, ch));
+          ldmatrix_x4_trans(qfr, sq + G::off(r, ch));
+          mma_bf16_16816(dv[db], pa, dofr[0], dofr[1]);
+          mma_bf16_16816(dv[db + 1], pa, dofr[2], dofr[3]);
+          mma_bf16_16816(dk[db], dsa, qfr[0], qfr[1]);
+          mma_bf16_16816(dk[db + 1], dsa, qfr[2], qfr[3]);
+        }
+      }
+    }
+    const int krow[2] = {key_base + (lane >> 2), key_base + (lane >> 2) + 8};
+    __nv_bfloat16* gdk = dqkv + static_cast<int64_t>(b) * T * ld + D + h * HD;
+    __nv_bfloat16* gdv = gdk + D;
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      if (krow[rr] >= T) continue;
+#pragma unroll
+      for (int db = 0; db < 8; ++db) {
+        const int64_t off = static_cast<int64_t>(krow[rr]) * ld + db * 8 + (lane & 3) * 2;
+        *reinterpret_cast<uint32_t*>(gdk + off) = pack_bf16(dk[db][2 * rr] * scale, dk[db][2 * rr + 1] * scale);
+        *reinterpret_cast<uint32_t*>(gdv + off) = pack_bf16(dv[db][2 * rr], dv[db][2 * rr + 1]);
+      }
+    }
+    if (dbias != nullptr) {
+#pragma unroll
+      for (int db = 0; db < 8; ++db) {
+        float c0 = dk[db][0] + dk[db][2], c1 = dk[db][1] + dk[db][3];
+        float e0 = dv[db][0] + dv[db][2], e1 = dv[db][1] + dv[db][3];
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+          c0 += __shfl_xor_sync(0xffffffffu, c0, o);
+          c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+          e0 += __shfl_xor_sync(0xffffffffu, e0, o);
+          e1 += __shfl_xor_sync(0xffffffffu, e1, o);
+        }
+        if (lane < 4) {
+          atomicAdd(&s_col[64 + db * 8 + lane * 2], c0 * scale);
+          atomicAdd(&s_col[64 + db * 8 + lane * 2 + 1], c1 * scale);
+          atomicAdd(&s_col[128 + db * 8 + lane * 2], e0);
+          atomicAdd(&s_col[128 + db * 8 + lane * 2 + 1], e1);
+        }
+      }
+      __syncthreads();
+      if (tid < 192) atomicAdd(dbias + (tid >> 6) * D + h * HD + (tid & 63), s_col[tid]);
+    }
+  }
+}
+
+static int launch_bwd_small(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int B,
+                            int T, int H, int w_left, int w_right, float* dbias, cudaStream_t st) {
+  constexpr int smem = 8 * Geo<64>::kTileBytes + 2 * kSmallT * 256 + 192 * static_cast<int>(sizeof(float));
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return set_error(-5, cudaGetErrorString(e));
+    configured = true;
+  }
+  const float scale = 0.125f;
+  const float scale_log2 = 1.4426950408889634f * scale;
+  attn_bwd_small_kernel<<<dim3(H, B), 256, smem, st>>>(
+      static_cast<const __nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(out),
+      static_cast<const __nv_bfloat16*>(dout), lse, static_cast<__nv_bfloat16*>(dqkv), T, H, w_left, w_right,
+      scale_log2, scale, dbias);
+  OSUDIT_CHECK_LAUNCH();
+  return 0;
+}
+
 template <int HD>
 static int launch_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, void* dqkv, int B,
                       int T, int H, int w_left, int w_right, float* dbias, cudaStream_t st) {
@@ -672,6 +954,12 @@ extern "C" int osudit_attn_band_bwd(const void* qkv, const void* out, const void
   if (w_left < 0 || w_left > T) w_left = T;
   if (w_right < 0 || w_right > T) w_right = T;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  static const bool use_small = [] {
+    const char* e = getenv("OSUDIT_ATTN_BWD_SMALL");
+    return !(e && e[0] == '0');
+  }();
+  if (head_dim == 64 && T <= kSmallT && use_small)  // the whole (sample, head) problem in one CTA
+    return launch_bwd_small(qkv, out, dout, lse, dqkv, B, T, H, w_left, w_right, dbias_qkv, st);
   if (head_dim == 64)
     return launch_bwd<64>(qkv, out, dout, lse, delta, dqkv, B, T, H, w_left, w_right, dbias_qkv, st);
   return launch_bwd<72>(qkv, out, dout, lse, delta, dqkv, B, T, H, w_left, w_right, dbias_qkv, st);

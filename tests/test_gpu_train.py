@@ -156,7 +156,10 @@ def test_final_layer_backward(D):
 
 
 @pytest.mark.parametrize("B,T,H,W,hd", [(2, 128, 3, None, 64), (1, 200, 2, None, 64), (2, 300, 2, 128, 64),
-                                        (1, 512, 1, 40, 64), (2, 200, 2, None, 72), (1, 300, 3, 128, 72)])
+                                        (1, 512, 1, 40, 64), (2, 200, 2, None, 72), (1, 300, 3, 128, 72),
+                                        # T <= 128, head_dim 64: the one-CTA-per-(sample, head) backward
+                                        (3, 128, 2, 40, 64), (2, 100, 3, None, 64), (2, 64, 1, None, 64),
+                                        (1, 33, 2, 8, 64), (2, 128, 2, None, 72)])
 def test_attention_backward(B, T, H, W, hd):
     D = H * hd
     qkv = bf(torch.randn(B * T, 3 * D, device=DEV))
