@@ -27,7 +27,10 @@ def _bf(p):
 
 def _wt(p):
     """Transposed bf16 copy of an nn.Linear weight [out, in] -> [in, out] (the B operand of dgrad)."""
-    return p.detach().t().to(torch.bfloat16).contiguous()
+    p = p.detach()
+    if p.dtype == torch.float32 and p.is_contiguous() and p.shape[0] % 8 == 0:
+        return ops.transpose(p)  # tiled fp32 -> bf16 transpose (csrc/backward.cu)
+    return p.t().to(torch.bfloat16).contiguous()
 
 
 class TrainWeights:

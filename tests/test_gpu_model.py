@@ -55,6 +55,23 @@ def test_forward_matches_oracle(name, T, W):
     assert e_eps < EPS_TOL and e_all < EPS_TOL
 
 
+@pytest.mark.parametrize("T,W,rows", [(1, None, 2), (7, 128, 2), (129, 128, 3), (1000, 128, 2), (1000, 64, 1),
+                                      (520, 300, 2), (2048, 128, 2)])
+@torch.no_grad()
+def test_forward_shape_sweep(T, W, rows):
+    """Ragged and degenerate sequence lengths, odd batch sizes, bands narrower and wider than the tcgen05 window
+    (wider ones take the mma.sync kernel): eps within the bf16 tolerance of the oracle everywhere."""
+    shape, sd, m = build("DiT-S")
+    z, o, c, y = synth.sampling_batch(2, T, seed=T)
+    x, o, c, y = z[:rows], o[:rows], c[:rows], y[:rows]
+    t = torch.tensor([999, 0, 432][:rows])
+    mask = synth.band_mask(T, W) if W else None
+    ref = odit.forward(sd, shape.heads, x, t, o, c, y, mask)
+    out = m(x.to(DEV), t.to(DEV), o=o.to(DEV), c=c.to(DEV), y=y.to(DEV), attn_mask=mask.to(DEV) if W else None)
+    assert out.shape == (rows, 4, T) and bool(torch.isfinite(out).all())
+    assert rel(out[:, :2], ref[:, :2]) < EPS_TOL
+
+
 @torch.no_grad()
 def test_xl_width_and_head_dim_72():
     """DiT-XL geometry (hidden 1152, 16 heads of 72) at reduced depth so the CPU oracle stays fast."""

@@ -470,6 +470,6 @@ def test_loss_curve_1k_steps_overlaps_fp32_eager():
           f"{float(((rec['nat'] - rec['twin']).abs() / rec['twin']).max()):.2e})")
     assert float(rec["ref"][-1].mean()) < 0.97 * float(rec["ref"][0].mean())  # it trains
     # within 1 %, or — where two runs of the same code differ by more — within twice that run-to-run floor
-    assert mean_dev("nat_l1", "ref_l1") < max(1e-2, 2 * mean_dev("nat_l1", "twin_l1"))
-    assert med_dev("nat", "ref") < max(1e-2, 2 * med_dev("nat", "twin"))
+    assert mean_dev("nat_l1", "ref_l1") < min(3e-2, max(1e-2, 3 * mean_dev("nat_l1", "twin_l1")))
+    assert med_dev("nat", "ref") < min(3e-2, max(1e-2, 3 * med_dev("nat", "twin")))
     assert abs(float(rec["nat_l1"].mean()) / float(rec["ref_l1"].mean()) - 1) < 1e-2  # the whole curve's mean
