@@ -175,9 +175,12 @@ def main():
     ap.add_argument("--model", default="DiT-B")
     ap.add_argument("--global-batch", type=int, default=256)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--seq-len", type=int, default=128, help="datapoints per training window (config 5: 512)")
     ap.add_argument("--fused-optimizer", action="store_true",
                     help="use osudit.optim.FusedAdamWEMA instead of torch.optim.AdamW + the update_ema loop")
     args = ap.parse_args()
+    global SEQ
+    SEQ = args.seq_len
     # stdout carries exactly ONE JSON line: keep the real stdout aside and point fd 1 at stderr, so that anything a
     # library writes to C stdout (NCCL prints its version banner there when NCCL_DEBUG is set) cannot precede it
     sys.stdout.flush()
