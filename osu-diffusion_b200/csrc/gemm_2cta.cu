@@ -228,6 +228,18 @@ gemm2_kernel(const __grid_constant__ Params p) {
     for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
       const int m0 = (tile / p.n_tiles) * (2 * BM) + static_cast<int>(rank) * BM;
       const int n0 = (tile % p.n_tiles) * BN;
+      // EPI_BF16_DGELU: this thread's 32 pre-activations (64 B of its row) per chunk come straight from global
+      // memory; they are fetched one chunk ahead (the first one before the wait for the accumulator) so that
+      // their latency hides behind the TMEM read and the arithmetic of the current chunk.
+      uint4 ax_next[4];
+      auto load_aux = [&](int c, uint4(&dst)[4]) {
+        const bool in = m0 + row < p.M;
+        const uint4* ap = reinterpret_cast<const uint4*>(p.aux + static_cast<int64_t>(in ? m0 + row : 0) * p.ld_aux +
+                                                         n0 + c * 64 + half * 32);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dst[j] = in ? __ldg(ap + j) : make_uint4(0u, 0u, 0u, 0u);
+      };
+      if (EPI == EPI_BF16_DGELU) load_aux(grp, ax_next);
       warp_mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN);
@@ -235,12 +247,10 @@ gemm2_kernel(const __grid_constant__ Params p) {
       for (int c = grp; c < kChunks; c += kEpiGroups) {
         const int ncol0 = n0 + c * 64;
         uint4 ax[4];
-        if (EPI == EPI_BF16_DGELU) {  // this thread's 32 pre-activations (64 B of its row), in flight before the TMEM wait
-          const bool in = m0 + row < p.M;
-          const uint4* ap = reinterpret_cast<const uint4*>(p.aux + static_cast<int64_t>(in ? m0 + row : 0) * p.ld_aux +
-                                                           ncol0 + half * 32);
+        if (EPI == EPI_BF16_DGELU) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) ax[j] = in ? __ldg(ap + j) : make_uint4(0u, 0u, 0u, 0u);
+          for (int j = 0; j < 4; ++j) ax[j] = ax_next[j];
+          if (c + kEpiGroups < kChunks) load_aux(c + kEpiGroups, ax_next);
         }
         uint32_t r[32];
         tmem_ld_32x32(t_row + static_cast<uint32_t>(c * 64 + half * 32), r);
