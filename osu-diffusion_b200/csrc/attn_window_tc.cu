@@ -108,6 +108,19 @@ __device__ __forceinline__ TileInfo decode_tile(const Params& p, int tile) {
 // far inside bf16/fp32 range, and the final O / sum is independent of the reference.
 constexpr float kJump = 24.0f;
 
+// Optional timeline instrumentation (build with -DOSUDIT_ATTN_TRACE): CTA 0 records clock64() at the hand-off
+// points of tiles 8..23 for the MMA warp (role 0), softmax half 0 (role 1) and half 1 (role 2);
+// osudit_debug_attn_trace() copies the table out.  Used to find the critical path, never in the shipped build.
+#ifdef OSUDIT_ATTN_TRACE
+__device__ long long g_trace[3 * 16 * 8];
+#define ATTN_TRACE(role, i, ev)                                                     \
+  do {                                                                              \
+    if (blockIdx.x == 0 && (i) >= 8 && (i) < 24) g_trace[((role) * 16 + (i) - 8) * 8 + (ev)] = clock64(); \
+  } while (0)
+#else
+#define ATTN_TRACE(role, i, ev) do {} while (0)
+#endif
+
 __global__ void __launch_bounds__(kThreads, 1) attn_window_kernel(const __grid_constant__ Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -221,20 +234,28 @@ __global__ void __launch_bounds__(kThreads, 1) attn_window_kernel(const __grid_c
       }
       for (int i = 0; i < n_my; ++i) {
         const bool has_next = i + 1 < n_my;
+        ATTN_TRACE(0, i, 0);
         if (has_next) {
           mbar_wait(qk_full, (i + 1) & 1);
+          ATTN_TRACE(0, i, 1);
           issue_s_slab(i + 1, 0);
         }
+        ATTN_TRACE(0, i, 2);
         mbar_wait(v_full, i & 1);
         mbar_wait(o_free, (i & 1) ^ 1);
+        ATTN_TRACE(0, i, 3);
         issue_pv_half(i, 0);
+        ATTN_TRACE(0, i, 4);
         if (has_next) {
           issue_s_slab(i + 1, 1);
           umma_commit(s01_done);
+          ATTN_TRACE(0, i, 5);
           issue_s_slab(i + 1, 2);
           umma_commit(s_done);
         }
+        ATTN_TRACE(0, i, 6);
         issue_pv_half(i, 1);
+        ATTN_TRACE(0, i, 7);
       }
     }
   } else {
@@ -344,9 +365,13 @@ __global__ void __launch_bounds__(kThreads, 1) attn_window_kernel(const __grid_c
       };
 
       // S slabs this half reads exist; PV_half(i-1) has finished reading this half's P blocks
+      const bool tracer = (quad == 0 && lane == 0);
+      if (tracer) ATTN_TRACE(1 + half, i, 0);
       mbar_wait(half == 0 ? s01_done : s_done, par);
+      if (tracer) ATTN_TRACE(1 + half, i, 1);
       if (i > 0) mbar_wait(&o_done[half], par ^ 1);
       tc_fence_after();
+      if (tracer) ATTN_TRACE(1 + half, i, 2);
 
       uint32_t ra[32], rb[32];
       if (in_range(cbeg)) tmem_ld_32x32(t_lane + kColS + cbeg * 32, ra);
@@ -367,6 +392,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_window_kernel(const __grid_c
         }
       }
       const float sum = (sum0 + sum1) + (sum2 + sum3);
+      if (tracer) ATTN_TRACE(1 + half, i, 3);
       float2* xc = xchg + par * 128;
       if (half == 0) {
         xc[row] = make_float2(ref, sum);
@@ -383,9 +409,11 @@ __global__ void __launch_bounds__(kThreads, 1) attn_window_kernel(const __grid_c
       const float2 other = xc[row];
 
       // ---- epilogue (half 1): (w0 O0 + w1 O1) / (w0 sum0 + w1 sum1) -> bf16 -> global
+      if (tracer) ATTN_TRACE(2, i, 4);
       mbar_wait(&o_done[0], par);
       mbar_wait(&o_done[1], par);
       tc_fence_after();
+      if (tracer) ATTN_TRACE(2, i, 5);
       const float rmax = fmaxf(other.x, ref);
       const float w_a = (other.x == -INFINITY) ? 0.f : fast_exp2(other.x - rmax);
       const float w_b = (ref == -INFINITY) ? 0.f : fast_exp2(ref - rmax);
@@ -402,6 +430,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_window_kernel(const __grid_c
         if (hh == 1) {
           tc_fence_before();
           mbar_arrive(o_free);
+          if (tracer) ATTN_TRACE(2, i, 6);
         }
         if (q < p.T) {
           auto mix = [&](int k) {
@@ -414,6 +443,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_window_kernel(const __grid_c
                            pack_bf16(mix(8 * j + 4), mix(8 * j + 5)), pack_bf16(mix(8 * j + 6), mix(8 * j + 7)));
         }
       }
+      if (tracer) ATTN_TRACE(2, i, 7);
     }
   }
 
@@ -426,6 +456,12 @@ __global__ void __launch_bounds__(kThreads, 1) attn_window_kernel(const __grid_c
 }
 
 }  // namespace attn_tc
+
+#ifdef OSUDIT_ATTN_TRACE
+extern "C" int osudit_debug_attn_trace(long long* host_out) {
+  return cudaMemcpyFromSymbol(host_out, attn_tc::g_trace, sizeof(attn_tc::g_trace)) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 // True when every key a 128-query tile may attend lies inside its [q0-128, q0+256) window.
 bool attn_window_applicable(int T, int head_dim, int w_left, int w_right, const uint8_t* mask) {
