@@ -86,9 +86,9 @@ int osudit_transpose_bf16(const void* in, void* out, int64_t rows, int64_t cols,
 int osudit_gelu(const void* pre, const void* dy, void* out, int64_t n, int backward, void* stream);
 
 /* Single-segment bf16 GEMM (as osudit_gemm_bf16) whose epilogue also touches a second bf16 [M, N] tensor `aux`:
- *   OSUDIT_EPI_BF16_GELU_SAVE: aux = A B^T + bias (the fc1 pre-activation, kept for the backward),
- *                              out = gelu_tanh(A B^T + bias)                   (training forward, models.py:112-119)
- *   OSUDIT_EPI_BF16_DGELU:     out = (A B^T) * gelu_tanh'(aux)                 (the gradient through that GELU)
+ *   OSUDIT_EPI_BF16_GELU_SAVE: out = gelu_tanh(A B^T + bias), aux = gelu_tanh'(A B^T + bias): all the backward needs
+ *                              from the fc1 pre-activation                     (training forward, models.py:112-119)
+ *   OSUDIT_EPI_BF16_DGELU:     out = (A B^T) * aux                             (the gradient through that GELU)
  * Fused into the CTA-pair kernel's epilogue where that kernel applies; two launches with the same result otherwise. */
 #define OSUDIT_EPI_BF16_GELU_SAVE 3
 #define OSUDIT_EPI_BF16_DGELU 4

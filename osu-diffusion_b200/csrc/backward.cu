@@ -115,6 +115,39 @@ gelu_kernel(const __nv_bfloat16* __restrict__ pre, const __nv_bfloat16* __restri
   reinterpret_cast<uint4*>(out)[i] = o;
 }
 
+// Two-launch path of osudit_gemm_bf16_aux (shapes the CTA-pair kernel does not take):
+// mode 0: out = gelu(aux), aux = gelu'(aux) in place;  mode 1: out = out * aux.
+__global__ void __launch_bounds__(256)
+gelu_aux_kernel(__nv_bfloat16* __restrict__ aux, __nv_bfloat16* __restrict__ out, int64_t n8, int mode) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  uint4 a = reinterpret_cast<const uint4*>(aux)[i];
+  uint4 o = mode ? reinterpret_cast<const uint4*>(out)[i] : make_uint4(0, 0, 0, 0);
+  uint32_t* aa = reinterpret_cast<uint32_t*>(&a);
+  uint32_t* oo = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 x = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&aa[k]));
+    if (mode == 0) {
+      oo[k] = pack_bf16(gelu_tanh_f(x.x), gelu_tanh_f(x.y));
+      aa[k] = pack_bf16(gelu_tanh_grad(x.x), gelu_tanh_grad(x.y));
+    } else {
+      const float2 y = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&oo[k]));
+      oo[k] = pack_bf16(y.x * x.x, y.y * x.y);
+    }
+  }
+  reinterpret_cast<uint4*>(out)[i] = o;
+  if (mode == 0) reinterpret_cast<uint4*>(aux)[i] = a;
+}
+
+int gelu_aux_launch(void* aux, void* out, int64_t n, int mode, cudaStream_t st) {
+  if (n <= 0 || (n % 8) != 0) return set_error(-1, "gelu_aux: element count must be a positive multiple of 8");
+  gelu_aux_kernel<<<static_cast<unsigned>((n / 8 + 255) / 256), 256, 0, st>>>(
+      static_cast<__nv_bfloat16*>(aux), static_cast<__nv_bfloat16*>(out), n / 8, mode);
+  OSUDIT_CHECK_LAUNCH();
+  return 0;
+}
+
 // out[r, c] = dy[r, c] * gelu'(pre[r, c]) and dbias[c] += sum_r out[r, c] (the fc1 bias gradient):
 // thread = 8 consecutive columns x kGeluRows rows, one atomic per column per CTA.
 constexpr int kGeluRows = 64;

@@ -50,14 +50,16 @@ struct Params {
   CUtensorMap tma_a, tma_b, tma_out, tma_aux;
   int kblocks, M, N, m_tiles, n_tiles;
   const float* bias;
-  const __nv_bfloat16* aux;  // EPI_BF16_DGELU: the saved pre-activation, read straight from global memory
+  const __nv_bfloat16* aux;  // EPI_BF16_DGELU: the saved GELU derivative, read straight from global memory
   int64_t ld_aux;
 };
 
-// EPI_BF16_GELU_SAVE (training forward of fc1): aux = acc + bias (the pre-activation the backward needs),
-// out = gelu(acc + bias) — two stores per chunk instead of a separate GELU pass over HBM.
-// EPI_BF16_DGELU (training backward through the GELU): out = acc * gelu'(aux), the data gradient of fc2
-// multiplied by the activation derivative in the epilogue, so du is never materialised.
+// EPI_BF16_GELU_SAVE (training forward of fc1): out = gelu(acc + bias) and aux = gelu'(acc + bias) — the only
+// thing the backward needs from the pre-activation, computed here from the same tanh — two stores per chunk
+// instead of a separate GELU pass over HBM.
+// EPI_BF16_DGELU (training backward through the GELU): out = acc * aux, the data gradient of fc2 multiplied by the
+// saved derivative in the epilogue (one multiply per element; ncu showed the tensor pipe at 43 % when the
+// derivative was recomputed here), so du is never materialised.
 enum : int { EPI_BF16 = 1, EPI_BF16_GELU = 2, EPI_BF16_GELU_SAVE = 3, EPI_BF16_DGELU = 4 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -113,14 +115,17 @@ __device__ __forceinline__ float gelu_tanh(float x) {
   return fmaf(hx, t, hx);
 }
 
-__device__ __forceinline__ float gelu_tanh_grad(float x) {
+// x -> gelu_tanh(x) (returned in place) and its derivative, from one tanh
+__device__ __forceinline__ float gelu_tanh_with_grad(float& x) {
   const float x2 = x * x;
   const float u = x * fmaf(x2, 0.044715f * 0.7978845608028654f, 0.7978845608028654f);
   float t;
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
   const float du = fmaf(x2, 3.0f * 0.044715f * 0.7978845608028654f, 0.7978845608028654f);
   const float hx = 0.5f * x;
-  return fmaf(hx * du, fmaf(-t, t, 1.0f), fmaf(0.5f, t, 0.5f));
+  const float d = fmaf(hx * du, fmaf(-t, t, 1.0f), fmaf(0.5f, t, 0.5f));
+  x = fmaf(hx, t, hx);
+  return d;
 }
 
 template <int EPI>
@@ -277,30 +282,36 @@ gemm2_kernel(const __grid_constant__ Params p) {
             const uint32_t* w = reinterpret_cast<const uint32_t*>(&ax[j]);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[k]));
-              v[8 * j + 2 * k] *= gelu_tanh_grad(x.x);
-              v[8 * j + 2 * k + 1] *= gelu_tanh_grad(x.y);
+              const float2 d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[k]));
+              v[8 * j + 2 * k] *= d.x;
+              v[8 * j + 2 * k + 1] *= d.y;
             }
           }
         }
-        constexpr int kPasses = EPI == EPI_BF16_GELU_SAVE ? 2 : 1;  // SAVE: the pre-activation first, then its GELU
+        constexpr int kPasses = EPI == EPI_BF16_GELU_SAVE ? 2 : 1;  // SAVE: the derivative first, then the GELU
+        float dv[EPI == EPI_BF16_GELU_SAVE ? 32 : 1];
+        if (EPI == EPI_BF16_GELU_SAVE) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) dv[i] = gelu_tanh_with_grad(v[i]);
+        }
 #pragma unroll
         for (int pass = 0; pass < kPasses; ++pass, ++chunk_ctr) {
           uint8_t* buf = my_staging + (chunk_ctr & 1) * kStagingBytes;
           if (ep_tid == 0) tma_store_wait_read<1>();
           named_bar_sync(1 + grp, 256);
           uint8_t* my_row = buf + row * 128;
-          if (EPI == EPI_BF16_GELU || (EPI == EPI_BF16_GELU_SAVE && pass == 1)) {
+          if (EPI == EPI_BF16_GELU) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = gelu_tanh(v[i]);
           }
+          const float* src = (EPI == EPI_BF16_GELU_SAVE && pass == 0) ? dv : v;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             uint4 o;
-            o.x = pack_bf16(v[8 * j + 0], v[8 * j + 1]);
-            o.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
-            o.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
-            o.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+            o.x = pack_bf16(src[8 * j + 0], src[8 * j + 1]);
+            o.y = pack_bf16(src[8 * j + 2], src[8 * j + 3]);
+            o.z = pack_bf16(src[8 * j + 4], src[8 * j + 5]);
+            o.w = pack_bf16(src[8 * j + 6], src[8 * j + 7]);
             const int jj = half * 4 + j;
             *reinterpret_cast<uint4*>(my_row + ((jj ^ (row & 7)) << 4)) = o;
           }

@@ -525,9 +525,9 @@ extern "C" int osudit_gemm_bf16(int nseg, const void* const* a, const int64_t* l
   return gemm_entry(nseg, a, lda, b, ldb, k, M, N, bias, epilogue, out, ldo, stream, 0);
 }
 
-extern "C" int osudit_gelu(const void* pre, const void* dy, void* out, int64_t n, int backward, void* stream);
-extern "C" int osudit_gelu_bwd(const void* pre, const void* dy, void* out, int64_t rows, int N, float* dbias,
-                               void* stream);
+namespace osudit {
+int gelu_aux_launch(void* aux, void* out, int64_t n, int mode, cudaStream_t st);  // backward.cu
+}
 
 extern "C" int osudit_gemm_bf16_aux(const void* a, int64_t lda, const void* b, int64_t ldb, int64_t K, int64_t M,
                                     int64_t N, const float* bias, int epilogue, void* out, int64_t ldo, void* aux,
@@ -550,11 +550,11 @@ extern "C" int osudit_gemm_bf16_aux(const void* a, int64_t lda, const void* b, i
   if (epilogue == 3) {
     int rc = gemm_entry(1, as, ldas, bs, ldbs, ks, M, N, bias, EPI_BF16, aux, ld_aux, stream, 0);
     if (rc) return rc;
-    return osudit_gelu(aux, nullptr, out, M * N, 0, stream);
+    return gelu_aux_launch(aux, out, M * N, 0, static_cast<cudaStream_t>(stream));
   }
   int rc = gemm_entry(1, as, ldas, bs, ldbs, ks, M, N, bias, EPI_BF16, out, ldo, stream, 0);
   if (rc) return rc;
-  return osudit_gelu_bwd(aux, out, out, M, static_cast<int>(N), nullptr, stream);
+  return gelu_aux_launch(aux, out, M * N, 1, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int osudit_gemm_bf16_splitk(int nseg, const void* const* a, const int64_t* lda,

@@ -60,7 +60,7 @@ EPI_BF16_GELU_SAVE, EPI_BF16_DGELU = 3, 4
 
 def gemm_aux(a, w, bias, epilogue: int, out, aux):
     """Single-segment bf16 GEMM out = f(a @ w.T + bias) with a second [M, N] bf16 tensor in the epilogue:
-    GELU_SAVE writes the pre-activation to `aux` and its GELU to `out`; DGELU multiplies by gelu'(aux)."""
+    GELU_SAVE writes gelu(pre) to `out` and gelu'(pre) to `aux`; DGELU multiplies the product by `aux`."""
     M, N = out.shape
     if a.shape[0] != M or w.shape[0] != N or a.shape[1] != w.shape[1] or tuple(aux.shape) != (M, N):
         raise _lib.OsuditError(f"gemm_aux: shape mismatch {tuple(a.shape)} x {tuple(w.shape)} -> {tuple(out.shape)}")

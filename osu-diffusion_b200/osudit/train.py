@@ -136,7 +136,7 @@ def forward_train(model, tw: TrainWeights, x, t, o, c, y, attn_mask):
         xb = _e(rows, D, dtype=torch.float32, device=dev)
         h2 = _e(rows, D, device=dev)
         ops.ln_modulate(xa, y1, mod, base + 2 * D, base + 3 * D, base + 4 * D, T, h2, x_out=xb)
-        pre = _e(rows, bw["fc1_w"].shape[0], device=dev)
+        pre = _e(rows, bw["fc1_w"].shape[0], device=dev)  # receives gelu'(fc1 output): what the backward needs of it
         u = ops.gemm_aux(h2, bw["fc1_w"], f32(blk.mlp.fc1.bias), ops.EPI_BF16_GELU_SAVE, torch.empty_like(pre), pre)
         y2 = _e(rows, D, device=dev)
         ops.gemm([u], [bw["fc2_w"]], f32(blk.mlp.fc2.bias), ops.EPI_BF16, y2)
@@ -194,7 +194,7 @@ def backward_train(model, tw: TrainWeights, S, dout):
         hidden = sv["pre"].shape[1]
         # ---- MLP branch: x_out = xb + gate_mlp * y2 (dy2 = gate_mlp * dx is already in dy_buf)
         grads[blk.mlp.fc2.weight] = _wgrad(dy2, sv["u"], dev)
-        # d pre = (dy2 W2) * gelu'(pre): the GELU derivative is applied in the data-gradient GEMM's epilogue
+        # d pre = (dy2 W2) * gelu'(pre): the saved derivative is applied in the data-gradient GEMM's epilogue
         dpre = ops.gemm_aux(dy2, bw["fc2_wt"], None, ops.EPI_BF16_DGELU, _e(rows, hidden, device=dev), sv["pre"])
         grads[blk.mlp.fc1.bias] = ops.colsum(dpre, z32(hidden))
         grads[blk.mlp.fc1.weight] = _wgrad(dpre, sv["h2"], dev)
