@@ -116,7 +116,7 @@ class DiT(nn.Module):
         self._engine = None
         self._train_weights = None
         # "bf16" (default: bf16 tensor-core operands, fp32 accumulate / residual / statistics; eps within 2e-3
-        # of the fp32 reference) or "fp32" (osudit/fp32.py: eps within 1e-5, inference only, ~8x slower)
+        # of the fp32 reference) or "fp32" (osudit/fp32.py: eps within 1e-5, inference only, ~17x slower)
         self.precision = os.environ.get("OSUDIT_PRECISION", "bf16")
 
     def initialize_weights(self):

@@ -5,7 +5,7 @@ Selected with `model.precision = "fp32"` (or OSUDIT_PRECISION=fp32 at constructi
 GEMM runs as six bf16 tensor-core products of three-way operand splits accumulated in one fp32 TMEM
 accumulator (csrc/fp32_mode.cu explains the layout); attention runs in fp32 on the CUDA cores.  This
 mode exists to validate checkpoints / kernels against the reference, it is not the benchmarked path
-(roughly 8x the bf16 mode's time).  Inference only.
+(an order of magnitude slower than the bf16 mode).  Inference only.
 """
 from __future__ import annotations
 
@@ -41,7 +41,9 @@ def pack_weight6(w):
     return torch.cat([hi, hi, hi, mid, mid, lo], dim=1).contiguous()
 
 
-KB_PER_SPLIT = 2  # 128 K-elements = 8 MMAs per tensor-core accumulation chain
+# 64-wide k-blocks per tensor-core accumulation chain: 8 (32 MMAs) keeps a GEMM within 6e-7 of fp64 (2: 1.5e-7) at a
+# quarter of the fp32 reduce-add traffic, which is what the fp32 mode's run time consists of
+KB_PER_SPLIT = 8
 
 
 def gemm_f32(a3, w6, bias, out, kb_per_split=None):
