@@ -177,7 +177,7 @@ class DiT(nn.Module):
         With autograd on (train.py:249-257) the call becomes one autograd node whose backward is the
         native schedule in osudit/train.py; under no_grad it is the inference schedule."""
         if self._needs_grad():
-            from osudit.train import DiTFunction, TrainWeights
+            from osudit.train import TrainWeights, dit_forward_train
             if self.precision != "bf16":
                 raise NotImplementedError("precision='fp32' is an inference mode; train with precision='bf16'")
             for name, v in (("x", x), ("t", t), ("o", o), ("c", c), ("y", y)):
@@ -186,10 +186,10 @@ class DiT(nn.Module):
                                        "on CUDA only and has no CPU fallback")
             if self._train_weights is None:
                 self._train_weights = TrainWeights()
-            tw = self._train_weights  # re-packed inside DiTFunction (eagerly, or as part of the CUDA graph)
-            return DiTFunction.apply(self, tw, x.detach().float().contiguous(), t.long().contiguous(),
+            tw = self._train_weights  # re-packed inside the head node (eagerly, or as part of the CUDA graph)
+            return dit_forward_train(self, tw, x.detach().float().contiguous(), t.long().contiguous(),
                                      o.float().contiguous(), c.float().contiguous(),
-                                     self._labels(y.long()).contiguous(), attn_mask, *self.parameters())
+                                     self._labels(y.long()).contiguous(), attn_mask)
         return self._raw_forward(x, t, o, c, y, attn_mask).clone()
 
     def forward_with_cfg(self, x, t, o, c, y, cfg_scale, attn_mask=None):

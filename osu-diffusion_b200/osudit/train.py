@@ -163,83 +163,111 @@ def _wgrad_small(dy_f32, x_bf16, dev):
     return _wgrad(dy_bf, x_bf16, dev)
 
 
-def backward_train(model, tw: TrainWeights, S, dout):
-    """Gradients of every trainable parameter, in `model.parameters()` order (None where frozen)."""
-    B, T, spec = S["B"], S["T"], S["spec"]
-    D, H, depth = model.hidden_size, model.num_heads, len(model.blocks)
+# ------------------------------------------------------------------------------ backward, in pieces
+# The backward runs as depth + 2 pieces — final layer, blocks from last to first, embedders ("head") — each of
+# which leaves the gradients of ITS parameters final.  One autograd node per piece (below) hands them to autograd
+# as soon as they exist, in the reverse registration order DistributedDataParallel builds its buckets in, so the
+# gradient all-reduce of a bucket overlaps the backward of the blocks before it (train.py:152,257).
+class _Bwd:
+    """Buffers shared by the pieces of one backward pass."""
+    __slots__ = ("dx", "dmod", "dy_buf", "dh_buf", "dy2")
+
+
+def _adaln_grads(S, dmod_cols, lin, dev):
+    """Gradients of one adaLN Linear (mod = SiLU(cond) W^T + b) from its finished columns of dmod."""
+    dm = dmod_cols.contiguous()
+    dm_bf, _ = ops.split_bf16(dm, need_lo=False)
+    gw = _wgrad(dm_bf, S["c_hi"], dev)
+    gb = ops.colsum(dm, torch.zeros(dm.shape[1], dtype=torch.float32, device=dev))
+    return {lin.weight: gw, lin.bias: gb}
+
+
+def bwd_final(model, tw: TrainWeights, S, dout):
+    """Final layer + the gate of the last block's MLP branch.  Returns (shared buffers, {param: grad})."""
+    B, T = S["B"], S["T"]
+    D, depth = model.hidden_size, len(model.blocks)
     rows, dev, mod = B * T, dout.device, S["mod"]
     z32 = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)  # noqa: E731
-    grads = {}
-    dmod = z32(B, mod.shape[1])
-    dx = _e(rows, D, dtype=torch.float32, device=dev)
-
+    bs, grads = _Bwd(), {}
+    bs.dmod = z32(B, mod.shape[1])
+    bs.dx = _e(rows, D, dtype=torch.float32, device=dev)
     fbase = 6 * D * depth
     fl = model.final_layer
     grads[fl.linear.weight], grads[fl.linear.bias] = z32(4, D), z32(4)
-    ops.final_layer_bwd(S["xf"], dout.contiguous(), mod, dmod, fbase, fbase + D, B, T,
+    ops.final_layer_bwd(S["xf"], dout.contiguous(), mod, bs.dmod, fbase, fbase + D, B, T,
                         fl.linear.weight.detach().float().contiguous(), grads[fl.linear.weight],
-                        grads[fl.linear.bias], dx)
-
+                        grads[fl.linear.bias], bs.dx)
+    grads.update(_adaln_grads(S, bs.dmod[:, fbase:fbase + 2 * D], fl.adaLN_modulation[1], dev))
     # Bias gradients are the column sums of the branch gradients and are accumulated by the kernels that
     # produce those.  Along the residual stream each LayerNorm backward is fused with the gated-residual
     # backward that follows it (ops.ln_gate_bwd); only the very first gate (last block's MLP) stands alone.
-    dy_buf, dh_buf = _e(rows, D, device=dev), _e(rows, D, device=dev)
+    bs.dy_buf, bs.dh_buf = _e(rows, D, device=dev), _e(rows, D, device=dev)
     last = model.blocks[depth - 1]
-    grads[last.mlp.fc2.bias] = z32(D)
-    dy2 = ops.gate_residual_bwd(dx, S["blocks"][depth - 1]["y2"], mod, dmod, 6 * D * (depth - 1) + 5 * D, B, T,
-                                dy_buf, dbias=grads[last.mlp.fc2.bias])
-    for i in reversed(range(depth)):
-        blk, bw, sv = model.blocks[i], tw.blocks[i], S["blocks"][i]
-        base = 6 * D * i
-        hidden = sv["pre"].shape[1]
-        # ---- MLP branch: x_out = xb + gate_mlp * y2 (dy2 = gate_mlp * dx is already in dy_buf)
-        grads[blk.mlp.fc2.weight] = _wgrad(dy2, sv["u"], dev)
-        # d pre = (dy2 W2) * gelu'(pre): the saved derivative is applied in the data-gradient GEMM's epilogue
-        dpre = ops.gemm_aux(dy2, bw["fc2_wt"], None, ops.EPI_BF16_DGELU, _e(rows, hidden, device=dev), sv["pre"])
-        grads[blk.mlp.fc1.bias] = ops.colsum(dpre, z32(hidden))
-        grads[blk.mlp.fc1.weight] = _wgrad(dpre, sv["h2"], dev)
-        dh2 = ops.gemm([dpre], [bw["fc1_wt"]], None, ops.EPI_BF16, dh_buf)
-        # ---- LN2 backward into dx, then the attention branch's gate: xb = xa + gate_msa * y1
-        grads[blk.attn.out_proj.bias] = z32(D)
-        dy1 = ops.ln_gate_bwd(sv["xb"], dh2, mod, dmod, base + 3 * D, base + 4 * D, B, T, dx, True,
-                              y=sv["y1"], gate_col=base + 2 * D, dy=dy_buf, dbias=grads[blk.attn.out_proj.bias])
-        grads[blk.attn.out_proj.weight] = _wgrad(dy1, sv["att"], dev)
-        datt = ops.gemm([dy1], [bw["out_wt"]], None, ops.EPI_BF16, dh_buf)
-        grads[blk.attn.in_proj_bias] = z32(3 * D)
-        dqkv = ops.attn_band_bwd(sv["qkv"], sv["att"], datt, sv["lse"], _e(rows, 3 * D, device=dev), B, T, H,
-                                 D // H, spec.w_left, spec.w_right, dbias=grads[blk.attn.in_proj_bias])
-        grads[blk.attn.in_proj_weight] = _wgrad(dqkv, sv["h1"], dev)
-        dh1 = ops.gemm([dqkv], [bw["qkv_wt"]], None, ops.EPI_BF16, dh_buf)
-        # ---- LN1 backward into dx, then the previous block's MLP gate
-        if i > 0:
-            prev = model.blocks[i - 1]
-            grads[prev.mlp.fc2.bias] = z32(D)
-            dy2 = ops.ln_gate_bwd(sv["xa"], dh1, mod, dmod, base, base + D, B, T, dx, True,
-                                  y=S["blocks"][i - 1]["y2"], gate_col=base - D, dy=dy_buf,
-                                  dbias=grads[prev.mlp.fc2.bias])
-        else:
-            ops.ln_gate_bwd(sv["xa"], dh1, mod, dmod, base, base + D, B, T, dx, True)
+    grads[last.mlp.fc2.bias] = z32(D)  # handed out by the last block's piece
+    bs.dy2 = ops.gate_residual_bwd(bs.dx, S["blocks"][depth - 1]["y2"], mod, bs.dmod, 6 * D * (depth - 1) + 5 * D,
+                                   B, T, bs.dy_buf, dbias=grads[last.mlp.fc2.bias])
+    return bs, grads
 
-    # ---- first layer: x0 = a W^T + b  (no gradient to the inputs)
+
+def bwd_block(model, tw: TrainWeights, S, bs, i, carry):
+    """Backward of block i.  `carry` holds fc2.bias of this block (accumulated by the previous piece); the
+    returned dict covers this block's parameters, and the new carry the fc2.bias of block i-1."""
+    B, T, spec = S["B"], S["T"], S["spec"]
+    D, H = model.hidden_size, model.num_heads
+    rows, dev, mod, dmod, dx = B * T, bs.dx.device, S["mod"], bs.dmod, bs.dx
+    z32 = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)  # noqa: E731
+    blk, bw, sv = model.blocks[i], tw.blocks[i], S["blocks"][i]
+    base = 6 * D * i
+    hidden = sv["pre"].shape[1]
+    grads = {blk.mlp.fc2.bias: carry}
+    dy2 = bs.dy2
+    # ---- MLP branch: x_out = xb + gate_mlp * y2 (dy2 = gate_mlp * dx is already in dy_buf)
+    grads[blk.mlp.fc2.weight] = _wgrad(dy2, sv["u"], dev)
+    # d pre = (dy2 W2) * gelu'(pre): the saved derivative is applied in the data-gradient GEMM's epilogue
+    dpre = ops.gemm_aux(dy2, bw["fc2_wt"], None, ops.EPI_BF16_DGELU, _e(rows, hidden, device=dev), sv["pre"])
+    grads[blk.mlp.fc1.bias] = ops.colsum(dpre, z32(hidden))
+    grads[blk.mlp.fc1.weight] = _wgrad(dpre, sv["h2"], dev)
+    dh2 = ops.gemm([dpre], [bw["fc1_wt"]], None, ops.EPI_BF16, bs.dh_buf)
+    # ---- LN2 backward into dx, then the attention branch's gate: xb = xa + gate_msa * y1
+    grads[blk.attn.out_proj.bias] = z32(D)
+    dy1 = ops.ln_gate_bwd(sv["xb"], dh2, mod, dmod, base + 3 * D, base + 4 * D, B, T, dx, True,
+                          y=sv["y1"], gate_col=base + 2 * D, dy=bs.dy_buf, dbias=grads[blk.attn.out_proj.bias])
+    grads[blk.attn.out_proj.weight] = _wgrad(dy1, sv["att"], dev)
+    datt = ops.gemm([dy1], [bw["out_wt"]], None, ops.EPI_BF16, bs.dh_buf)
+    grads[blk.attn.in_proj_bias] = z32(3 * D)
+    dqkv = ops.attn_band_bwd(sv["qkv"], sv["att"], datt, sv["lse"], _e(rows, 3 * D, device=dev), B, T, H,
+                             D // H, spec.w_left, spec.w_right, dbias=grads[blk.attn.in_proj_bias])
+    grads[blk.attn.in_proj_weight] = _wgrad(dqkv, sv["h1"], dev)
+    dh1 = ops.gemm([dqkv], [bw["qkv_wt"]], None, ops.EPI_BF16, bs.dh_buf)
+    # ---- LN1 backward into dx, then the previous block's MLP gate
+    new_carry = None
+    if i > 0:
+        new_carry = z32(D)
+        bs.dy2 = ops.ln_gate_bwd(sv["xa"], dh1, mod, dmod, base, base + D, B, T, dx, True,
+                                 y=S["blocks"][i - 1]["y2"], gate_col=base - D, dy=bs.dy_buf, dbias=new_carry)
+    else:
+        ops.ln_gate_bwd(sv["xa"], dh1, mod, dmod, base, base + D, B, T, dx, True)
+    # every column of this block's slice of dmod is final now (its MLP gate was accumulated one piece earlier)
+    grads.update(_adaln_grads(S, dmod[:, base:base + 6 * D], blk.adaLN_modulation[1], dev))
+    return grads, new_carry
+
+
+def bwd_head(model, tw: TrainWeights, S, bs):
+    """First layer (no gradient to the inputs) and the conditioning path: s = SiLU(temb + table[y]),
+    temb = SiLU(tf W0^T + b0) W2^T + b2."""
+    B = S["B"]
+    D = model.hidden_size
+    dev, dx, dmod = bs.dx.device, bs.dx, bs.dmod
+    z32 = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)  # noqa: E731
+    grads = {}
     first = model.xoc_embedder.mlp[0]
     grads[first.weight] = _wgrad_small(dx, S["a_hi"], dev)
     grads[first.bias] = ops.colsum(dx, z32(D))
-
-    # ---- conditioning path: mod = s Wmod^T + bmod, s = SiLU(temb + table[y])
     dmod_bf, _ = ops.split_bf16(dmod, need_lo=False)
-    gw = _wgrad(dmod_bf, S["c_hi"], dev)
-    gb = ops.colsum(dmod, z32(mod.shape[1]))
-    mods = [b.adaLN_modulation[1] for b in model.blocks] + [fl.adaLN_modulation[1]]
-    r0 = 0
-    for m in mods:
-        n = m.weight.shape[0]
-        grads[m.weight], grads[m.bias] = gw[r0:r0 + n], gb[r0:r0 + n]
-        r0 += n
     ds = ops.gemm([dmod_bf], [tw.mod_wt], None, ops.EPI_F32, _e(B, D, dtype=torch.float32, device=dev))
     table_p = model.y_embedder.embedding_table.weight
     grads[table_p] = z32(*table_p.shape)
     dcond = ops.silu_bwd(S["temb"], ds, torch.empty_like(ds), table=S["table"], y=S["y"], dtable=grads[table_p])
-    # t-MLP: temb = SiLU(tf W0^T + b0) W2^T + b2
     t0, t2 = model.t_embedder.mlp[0], model.t_embedder.mlp[2]
     dcond_bf, _ = ops.split_bf16(dcond, need_lo=False)
     grads[t2.weight] = _wgrad(dcond_bf, S["s1_hi"], dev)
@@ -248,19 +276,40 @@ def backward_train(model, tw: TrainWeights, S, dout):
     dh1t = ops.silu_bwd(S["h1t"], ds1, torch.empty_like(ds1))
     grads[t0.weight] = _wgrad_small(dh1t, S["tf_hi"], dev)
     grads[t0.bias] = ops.colsum(dh1t, z32(D))
-    return [grads.get(p) if p.requires_grad else None for p in model.parameters()]
+    return grads
+
+
+def param_groups(model):
+    """(head, [block 0..L-1], final): the parameters each backward piece is responsible for."""
+    head = [p for m in (model.xoc_embedder, model.t_embedder, model.y_embedder) for p in m.parameters()]
+    return head, [list(b.parameters()) for b in model.blocks], list(model.final_layer.parameters())
+
+
+def _pick(grads, params):
+    return [grads.get(p) if p.requires_grad else None for p in params]
+
+
+def backward_train(model, tw: TrainWeights, S, dout):
+    """All pieces in order: gradients of every trainable parameter in `model.parameters()` order."""
+    bs, grads = bwd_final(model, tw, S, dout)
+    carry = grads.pop(model.blocks[-1].mlp.fc2.bias)
+    for i in reversed(range(len(model.blocks))):
+        g, carry = bwd_block(model, tw, S, bs, i, carry)
+        grads.update(g)
+    grads.update(bwd_head(model, tw, S, bs))
+    return _pick(grads, model.parameters())
 
 
 class TrainGraph:
     """CUDA-graph replay of one training step's model work for a fixed (model, batch shape, mask).
 
     A config-3 step (DiT-B, 256 x 128 datapoints) is ~370 launches of 10-300 us each plus ~300 small
-    allocations: eager, the host needs longer to enqueue them than the GPU needs to run them.  Two graphs are
-    captured once — (weight re-pack + forward_train) and backward_train, sharing one memory pool so the saved
-    activations stay where the backward graph expects them — and replayed every step with only the inputs and
-    the incoming output gradient copied into static buffers.  The weight copies are rebuilt INSIDE the forward
+    allocations: eager, the host needs longer to enqueue them than the GPU needs to run them.  The graphs are
+    captured once — (weight re-pack + forward_train), then one per backward piece, all sharing one memory pool so
+    the saved activations stay where the backward graphs expect them — and replayed every step with only the inputs
+    and the incoming output gradient copied into static buffers.  The weight copies are rebuilt INSIDE the forward
     graph from the live fp32 parameters (same addresses every step), so optimizer updates need no re-capture.
-    The returned gradient tensors are the graph's static buffers; autograd / DDP copy out of them (they never
+    The returned gradient tensors are the graphs' static buffers; autograd / DDP copy out of them (they never
     take ownership because this object also references them).
     """
 
@@ -270,7 +319,8 @@ class TrainGraph:
         self.inputs = [v.clone() for v in (x, t, o, c, y)]
         self.tw = TrainWeights()
         self.sig = self.signature(model)
-        self.pending = None  # weakref to the autograd ctx whose backward has not run yet
+        self.pending = None  # weakref to the call whose backward has not finished yet
+        head, blocks, final = param_groups(model)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side), torch.no_grad():  # eager warm-up: host-side caches, function attributes
@@ -284,10 +334,22 @@ class TrainGraph:
             self.tw.sig = None
             self.tw.refresh(model)
             self.out, self.S = forward_train(model, self.tw, *self.inputs, attn_mask)
+        pool = self.g_fwd.pool()
         self.dout = torch.zeros_like(self.out)
-        self.g_bwd = torch.cuda.CUDAGraph()
-        with torch.no_grad(), torch.cuda.graph(self.g_bwd, pool=self.g_fwd.pool()):
-            self.grads = backward_train(model, self.tw, self.S, self.dout)
+        self.g_final = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(self.g_final, pool=pool):
+            self.bs, g = bwd_final(model, self.tw, self.S, self.dout)
+            carry = g.pop(model.blocks[-1].mlp.fc2.bias)
+            self.grads_final = _pick(g, final)
+        self.g_block, self.grads_block = {}, {}
+        for i in reversed(range(len(model.blocks))):
+            self.g_block[i] = torch.cuda.CUDAGraph()
+            with torch.no_grad(), torch.cuda.graph(self.g_block[i], pool=pool):
+                g, carry = bwd_block(model, self.tw, self.S, self.bs, i, carry)
+                self.grads_block[i] = _pick(g, blocks[i])
+        self.g_head = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(self.g_head, pool=pool):
+            self.grads_head = _pick(bwd_head(model, self.tw, self.S, self.bs), head)
 
     @staticmethod
     def signature(model):
@@ -301,21 +363,26 @@ class TrainGraph:
             return False
         return True
 
-    def run_forward(self, ctx, x, t, o, c, y):
+    def run_forward(self, call, x, t, o, c, y):
         for dst, src in zip(self.inputs, (x, t, o, c, y)):
             dst.copy_(src)
         self.g_fwd.replay()
-        try:
-            self.pending = weakref.ref(ctx)
-        except TypeError:
-            self.pending = None
+        self.pending = weakref.ref(call)
         return self.out.clone()
 
-    def run_backward(self, dout):
+    def run_final(self, dout):
         self.dout.copy_(dout)
-        self.g_bwd.replay()
+        self.g_final.replay()
+        return self.grads_final
+
+    def run_block(self, i):
+        self.g_block[i].replay()
+        return self.grads_block[i]
+
+    def run_head(self):
+        self.g_head.replay()
         self.pending = None
-        return self.grads
+        return self.grads_head
 
 
 _GRAPHS_ENABLED = os.environ.get("OSUDIT_CUDA_GRAPHS", "1") != "0"
@@ -341,29 +408,90 @@ def _train_graph_for(model, x, t, o, c, y, attn_mask):
     return None if g.busy() else g
 
 
-class DiTFunction(torch.autograd.Function):
-    """out = DiT(x, t, o, c, y) with parameter gradients from the native backward."""
+class _Call:
+    """What the autograd nodes of one forward call share."""
+    __slots__ = ("model", "tw", "graph", "S", "bs", "carry", "__weakref__")
+
+
+class _HeadFn(torch.autograd.Function):
+    """Runs the whole forward; its backward is the LAST piece (first layer + conditioning path)."""
 
     @staticmethod
-    def forward(ctx, model, tw, x, t, o, c, y, attn_mask, *params):
-        ctx.model = model
-        ctx.graph = _train_graph_for(model, x, t, o, c, y, attn_mask)
-        if ctx.graph is not None:
-            return ctx.graph.run_forward(ctx, x, t, o, c, y)
-        tw.refresh(model)
-        out, saved = forward_train(model, tw, x, t, o, c, y, attn_mask)
-        ctx.tw, ctx.saved = tw, saved
+    def forward(ctx, call, x, t, o, c, y, attn_mask, *params):
+        model = call.model
+        ctx.call = call
+        call.graph = _train_graph_for(model, x, t, o, c, y, attn_mask)
+        if call.graph is not None:
+            return call.graph.run_forward(call, x, t, o, c, y)
+        call.tw.refresh(model)
+        out, call.S = forward_train(model, call.tw, x, t, o, c, y, attn_mask)
         return out
 
     @staticmethod
-    def backward(ctx, dout):
+    def backward(ctx, g):
+        call = ctx.call
+        head = param_groups(call.model)[0]
         with torch.no_grad():
-            if ctx.graph is not None:
-                grads = ctx.graph.run_backward(dout.float())
+            if call.graph is not None:
+                grads = call.graph.run_head()
             else:
-                grads = backward_train(ctx.model, ctx.tw, ctx.saved, dout.float())
-                ctx.saved = None
-        return (None,) * 8 + tuple(grads)
+                grads = _pick(bwd_head(call.model, call.tw, call.S, call.bs), head)
+                call.S = call.bs = None
+        return (None,) * 7 + tuple(grads)
+
+
+class _BlockFn(torch.autograd.Function):
+    """Identity in the forward; the backward of block i, returning that block's parameter gradients."""
+
+    @staticmethod
+    def forward(ctx, tok, call, i, *params):
+        ctx.call, ctx.i = call, i
+        return tok.view_as(tok)
+
+    @staticmethod
+    def backward(ctx, g):
+        call, i = ctx.call, ctx.i
+        with torch.no_grad():
+            if call.graph is not None:
+                grads = call.graph.run_block(i)
+            else:
+                gd, call.carry = bwd_block(call.model, call.tw, call.S, call.bs, i, call.carry)
+                grads = _pick(gd, list(call.model.blocks[i].parameters()))
+        return (g, None, None) + tuple(grads)
+
+
+class _FinalFn(torch.autograd.Function):
+    """Identity in the forward; the FIRST backward piece (final layer), which receives d loss / d out."""
+
+    @staticmethod
+    def forward(ctx, tok, call, *params):
+        ctx.call = call
+        return tok.view_as(tok)
+
+    @staticmethod
+    def backward(ctx, g):
+        call = ctx.call
+        model = call.model
+        with torch.no_grad():
+            if call.graph is not None:
+                grads = call.graph.run_final(g.float())
+            else:
+                call.bs, gd = bwd_final(model, call.tw, call.S, g.float())
+                call.carry = gd.pop(model.blocks[-1].mlp.fc2.bias)
+                grads = _pick(gd, list(model.final_layer.parameters()))
+        return (g, None) + tuple(grads)
+
+
+def dit_forward_train(model, tw, x, t, o, c, y, attn_mask):
+    """out = DiT(x, t, o, c, y) as a chain of autograd nodes over one native forward: head -> block 0 -> ... ->
+    block L-1 -> final.  Autograd walks it backwards, so parameter gradients are released group by group."""
+    call = _Call()
+    call.model, call.tw, call.graph, call.S, call.bs, call.carry = model, tw, None, None, None, None
+    head, blocks, final = param_groups(model)
+    tok = _HeadFn.apply(call, x, t, o, c, y, attn_mask, *head)
+    for i, ps in enumerate(blocks):
+        tok = _BlockFn.apply(tok, call, i, *ps)
+    return _FinalFn.apply(tok, call, *final)
 
 
 class LossFunction(torch.autograd.Function):
