@@ -1,9 +1,10 @@
-"""Training-time forward (activations kept) and backward of the DiT, as one autograd node.
+"""Training-time forward (activations kept) and backward of the DiT.
 
 The reference gets its gradients from PyTorch autograd over `DiT.forward` (train.py:249-257).  Here the
-whole model is a single `torch.autograd.Function` whose forward and backward are fixed schedules of
-libosudit launches: autograd, DDP and the optimizer see the same leaf parameters and receive fp32
-gradients for them, nothing else runs in torch.
+forward is one fixed schedule of libosudit launches and the backward another, cut into depth + 2 pieces
+(final layer, blocks, embedders) that hang off a chain of identity autograd nodes: autograd, DDP and the
+optimizer see the same leaf parameters and receive fp32 gradients for them group by group, nothing else
+runs in torch.
 
 Data-gradient GEMMs use transposed weight copies, weight-gradient GEMMs use transposed activations
 (`ops.transpose` pads the token dimension to a multiple of 8 with zeros); both then run on the same
