@@ -82,6 +82,11 @@ def _key(diffusion, module, uses_cfg, x, kw, clip):
             module.training, getattr(module, "precision", "bf16"))
 
 
+def release_graphs():
+    """Drop every captured sampling step (each one pins its static buffers and the model it was captured for)."""
+    _cache.clear()
+
+
 def step(diffusion, module, uses_cfg, x, t, kw, clip):
     """(sample, pred_xstart) of one reverse step through a cached graph."""
     key = _key(diffusion, module, uses_cfg, x, kw, clip)

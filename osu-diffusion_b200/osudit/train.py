@@ -390,6 +390,11 @@ _GRAPHS_ENABLED = os.environ.get("OSUDIT_CUDA_GRAPHS", "1") != "0"
 _train_graphs: dict = {}
 
 
+def release_graphs():
+    """Drop every captured training graph (and the activations / gradient buffers its memory pool pins)."""
+    _train_graphs.clear()
+
+
 def _train_graph_for(model, x, t, o, c, y, attn_mask):
     """The cached TrainGraph for this call, a new one, or None (disabled / saved activations still in use)."""
     if not _GRAPHS_ENABLED or torch.cuda.is_current_stream_capturing():
