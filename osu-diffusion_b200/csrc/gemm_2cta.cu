@@ -13,6 +13,7 @@
 //   peer CTA    epilogue warps arrive remotely (mapa) on the leader's tmem_empty barrier
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -44,7 +45,8 @@ constexpr int kBytesB = (BN / 2) * BK * 2;
 constexpr int kStageBytes = kBytesA + kBytesB;  // 32 KB per CTA
 constexpr int kStagingBytes = BM * 128;
 constexpr int kThreads = 64 + 256 * kEpiGroups;
-constexpr int kSmemBytes = kStages * kStageBytes + 2 * kEpiGroups * kStagingBytes + 1024;
+constexpr int kBiasBytes = kEpiGroups * 2 * BN * 4;  // bias slice of the current / next tile, per epilogue group
+constexpr int kSmemBytes = kStages * kStageBytes + 2 * kEpiGroups * kStagingBytes + 1024 + kBiasBytes;
 
 struct Params {
   CUtensorMap tma_a, tma_b, tma_out, tma_aux;
@@ -76,8 +78,10 @@ __device__ __forceinline__ uint32_t mapa_rank0(uint32_t smem_addr) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(smem_addr));
   return r;
 }
+// Default semantics (release at CTA scope), as the TMEM hand-off needs no memory ordering beyond the tcgen05 fences:
+// the explicit .release.cluster form cost ~2 400 cycles per tile on the epilogue's critical path (tools/gemm_trace.py).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const void* tmap, uint32_t leader_bar,
                                                  int32_t c0, int32_t c1) {
@@ -115,6 +119,20 @@ __device__ __forceinline__ float gelu_tanh(float x) {
   return fmaf(hx, t, hx);
 }
 
+// Two GELUs at once in half2 arithmetic (5 HFMA2-pipe instructions + one tanh.approx.f16x2 for the pair instead of
+// 2 x (5 + 1) in fp32): the result is rounded to bf16 (8 mantissa bits) right after, fp16 carries 11.
+__device__ __forceinline__ uint32_t gelu_tanh_pair(float a, float b) {
+  const __half2 x = __floats2half2_rn(a, b);
+  const __half2 x2 = __hmul2(x, x);  // overflows to inf for |x| > 255: tanh(+-inf) = +-1 gives x or 0, as it should
+  const __half2 pz = __hfma2(x2, __float2half2_rn(0.044715f * 0.7978845608028654f), __float2half2_rn(0.7978845608028654f));
+  const __half2 u = __hmul2(x, pz);
+  uint32_t t;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(*reinterpret_cast<const uint32_t*>(&u)));
+  const __half2 hx = __hmul2(x, __float2half2_rn(0.5f));
+  const float2 g = __half22float2(__hfma2(hx, *reinterpret_cast<const __half2*>(&t), hx));
+  return pack_bf16(g.x, g.y);
+}
+
 // x -> gelu_tanh(x) (returned in place) and its derivative, from one tanh
 __device__ __forceinline__ float gelu_tanh_with_grad(float& x) {
   const float x2 = x * x;
@@ -128,6 +146,19 @@ __device__ __forceinline__ float gelu_tanh_with_grad(float& x) {
   return d;
 }
 
+// Optional timeline instrumentation (build with -DOSUDIT_GEMM_TRACE): CTA 0 records clock64() for tiles 4..11 —
+// role 0 = MMA issuer (tile start / all MMAs issued), role 1 = epilogue thread 0 (per tile: accumulator ready, then
+// per chunk: buffer free, TMEM read done, tile stored to smem, TMA store issued).  osudit_debug_gemm_trace() copies it out.
+#ifdef OSUDIT_GEMM_TRACE
+__device__ long long g_gemm_trace[2 * 8 * 20];
+#define GEMM_TRACE(role, it, ev)                                                                    \
+  do {                                                                                              \
+    if (blockIdx.x == 0 && (it) >= 4 && (it) < 12) g_gemm_trace[((role) * 8 + (it) - 4) * 20 + (ev)] = clock64(); \
+  } while (0)
+#else
+#define GEMM_TRACE(role, it, ev) do {} while (0)
+#endif
+
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm2_kernel(const __grid_constant__ Params p) {
@@ -138,6 +169,7 @@ gemm2_kernel(const __grid_constant__ Params p) {
   uint64_t* tmem_full = empty_bar + kStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* s_bias_all = reinterpret_cast<float*>(staging + 2 * kEpiGroups * kStagingBytes + 1024);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -197,9 +229,12 @@ gemm2_kernel(const __grid_constant__ Params p) {
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
+      int it = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++it) {
+        GEMM_TRACE(0, it, 0);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
+        GEMM_TRACE(0, it, 1);
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
         for (int kb = 0; kb < p.kblocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
@@ -214,6 +249,7 @@ gemm2_kernel(const __grid_constant__ Params p) {
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
         umma_commit_pair(&tmem_full[acc]);
+        GEMM_TRACE(0, it, 2);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -230,7 +266,8 @@ gemm2_kernel(const __grid_constant__ Params p) {
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t chunk_ctr = 0;
-    for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
+    int it = 0;
+    for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++it) {
       const int m0 = (tile / p.n_tiles) * (2 * BM) + static_cast<int>(rank) * BM;
       const int n0 = (tile % p.n_tiles) * BN;
       // EPI_BF16_DGELU: this thread's 32 pre-activations (64 B of its row) per chunk come straight from global
@@ -245,8 +282,15 @@ gemm2_kernel(const __grid_constant__ Params p) {
         for (int j = 0; j < 4; ++j) dst[j] = in ? __ldg(ap + j) : make_uint4(0u, 0u, 0u, 0u);
       };
       if (EPI == EPI_BF16_DGELU) load_aux(grp, ax_next);
+      // this tile's 256 bias values go through shared memory (one global load per thread per tile, issued before
+      // the wait for the accumulator) instead of 8 dependent __ldg per thread per chunk on the critical path
+      float* s_bias = s_bias_all + (grp * 2 + (it & 1)) * BN;
+      s_bias[ep_tid] = p.bias != nullptr ? __ldg(p.bias + n0 + ep_tid) : 0.f;
+      if (ep_tid == 0) GEMM_TRACE(1, it, 0);
       warp_mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
+      named_bar_sync(1 + grp, 256);
+      if (ep_tid == 0) GEMM_TRACE(1, it, 1);
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BN);
 #pragma unroll 1
       for (int c = grp; c < kChunks; c += kEpiGroups) {
@@ -258,19 +302,20 @@ gemm2_kernel(const __grid_constant__ Params p) {
           if (c + kEpiGroups < kChunks) load_aux(c + kEpiGroups, ax_next);
         }
         uint32_t r[32];
+        if (ep_tid == 0) GEMM_TRACE(1, it, 2 + 4 * c);
         tmem_ld_32x32(t_row + static_cast<uint32_t>(c * 64 + half * 32), r);
         tmem_ld_wait();
         if (c + kEpiGroups >= kChunks) {  // this warp's last read of the accumulator: hand the stage back
           tc_fence_before();
+          if (ep_tid == 0 && c == 3) GEMM_TRACE(1, it, 18);
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(mapa_rank0(smem_u32(&tmem_empty[acc])));
         }
+        if (ep_tid == 0 && c == 3) GEMM_TRACE(1, it, 19);
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
-          const int n = ncol0 + half * 32 + i;
-          float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.bias != nullptr && n + 3 < p.N) b = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+          const float4 b = *reinterpret_cast<const float4*>(s_bias + c * 64 + half * 32 + i);
           v[i + 0] = __uint_as_float(r[i + 0]) + b.x;
           v[i + 1] = __uint_as_float(r[i + 1]) + b.y;
           v[i + 2] = __uint_as_float(r[i + 2]) + b.z;
@@ -299,28 +344,45 @@ gemm2_kernel(const __grid_constant__ Params p) {
           uint8_t* buf = my_staging + (chunk_ctr & 1) * kStagingBytes;
           if (ep_tid == 0) tma_store_wait_read<1>();
           named_bar_sync(1 + grp, 256);
+          if (ep_tid == 0) GEMM_TRACE(1, it, 2 + 4 * c + 1);
           uint8_t* my_row = buf + row * 128;
+#ifndef OSUDIT_GELU_H2
           if (EPI == EPI_BF16_GELU) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = gelu_tanh(v[i]);
           }
+#endif
           const float* src = (EPI == EPI_BF16_GELU_SAVE && pass == 0) ? dv : v;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             uint4 o;
-            o.x = pack_bf16(src[8 * j + 0], src[8 * j + 1]);
-            o.y = pack_bf16(src[8 * j + 2], src[8 * j + 3]);
-            o.z = pack_bf16(src[8 * j + 4], src[8 * j + 5]);
-            o.w = pack_bf16(src[8 * j + 6], src[8 * j + 7]);
+#ifdef OSUDIT_GELU_H2
+            if (EPI == EPI_BF16_GELU) {
+              o.x = gelu_tanh_pair(src[8 * j + 0], src[8 * j + 1]);
+              o.y = gelu_tanh_pair(src[8 * j + 2], src[8 * j + 3]);
+              o.z = gelu_tanh_pair(src[8 * j + 4], src[8 * j + 5]);
+              o.w = gelu_tanh_pair(src[8 * j + 6], src[8 * j + 7]);
+            } else
+#endif
+            {
+              o.x = pack_bf16(src[8 * j + 0], src[8 * j + 1]);
+              o.y = pack_bf16(src[8 * j + 2], src[8 * j + 3]);
+              o.z = pack_bf16(src[8 * j + 4], src[8 * j + 5]);
+              o.w = pack_bf16(src[8 * j + 6], src[8 * j + 7]);
+            }
             const int jj = half * 4 + j;
             *reinterpret_cast<uint4*>(my_row + ((jj ^ (row & 7)) << 4)) = o;
           }
+          if (ep_tid == 0) GEMM_TRACE(1, it, 2 + 4 * c + 2);
           fence_proxy_async_smem();
           named_bar_sync(1 + grp, 256);
+          if (ep_tid == 0) GEMM_TRACE(1, it, 2 + 4 * c + 3);
+#ifndef OSUDIT_GEMM_NOSTORE  // (timing experiment: the epilogue without its global writes)
           if (ep_tid == 0) {
             tma_store_2d((EPI == EPI_BF16_GELU_SAVE && pass == 0) ? &p.tma_aux : &p.tma_out, buf, ncol0, m0);
             tma_store_commit();
           }
+#endif
         }
       }
       acc ^= 1;
@@ -355,6 +417,12 @@ static int launch2(const Params& p, cudaStream_t stream) {
 }
 
 }  // namespace g2
+
+#ifdef OSUDIT_GEMM_TRACE
+extern "C" int osudit_debug_gemm_trace(long long* host_out) {
+  return cudaMemcpyFromSymbol(host_out, g2::g_gemm_trace, sizeof(g2::g_gemm_trace)) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 bool gemm_2cta_applicable(int nseg, int64_t M, int64_t N, int epilogue) {
   return nseg == 1 && epilogue >= g2::EPI_BF16 && epilogue <= g2::EPI_BF16_DGELU && N % 256 == 0 &&
