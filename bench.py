@@ -31,7 +31,7 @@ import torch  # noqa: E402
 
 MODEL, N_BEATMAPS, SEQ, STEPS_DIFF, CFG, BAND = "DiT-B", 64, 2048, 100, 1.5, 128
 METRIC = "beatmaps/sec DiT-B 100-step CFG sampling"
-NCU_GEMM_TRAFFIC_GB = 1.59  # ncu --set full, profiles/r01b_summary.md: (1.562 + 0.764 + 1.964 + 2.069) / 4
+NCU_GEMM_TRAFFIC_GB = 1.57  # ncu --set full, profiles/r01d_summary.md: (1.560 + 0.765 + 1.963 + 2.011) / 4
 UNIT = "beatmaps/s"
 
 
@@ -270,7 +270,7 @@ def kernel_roofline(model, diffusion, zd, od, cd, yd, mask_d, device):
             "launches)",
             "achieved": round(ach, 1), "peak": tf_peak, "unit": "TFLOP/s", "frac": round(ach / tf_peak, 4),
             "traffic": NCU_GEMM_TRAFFIC_GB, "traffic_unit": "GB per launch (dram read+write, mean of the QKV/out-proj/"
-            "fc1/fc2 launches in profiles/r01b_summary.md; algorithmic 1.56)", "peak_source": src, "launches_timed": n,
+            "fc1/fc2 launches in profiles/r01d_summary.md; algorithmic 1.56)", "peak_source": src, "launches_timed": n,
             "avg_launch_ms": round(ms / max(n, 1), 4), "share_of_step": round(ms / step_ms, 3),
             "per_shape_tflops": {k: round(v[0] / (v[1] / 1e3) / 1e12, 1) for k, v in by_shape.items()},
             "hbm_kernel": {"kernel": "ln_modulate_kernel", "bound": "hbm",
