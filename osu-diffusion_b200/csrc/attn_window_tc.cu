@@ -113,12 +113,18 @@ constexpr float kJump = 24.0f;
 // osudit_debug_attn_trace() copies the table out.  Used to find the critical path, never in the shipped build.
 #ifdef OSUDIT_ATTN_TRACE
 __device__ long long g_trace[3 * 16 * 8];
+__device__ long long g_trace_chunks[16 * 16];  // half 0, quadrant 0: per chunk (after the TMEM wait, after emit)
+#define ATTN_TRACE_CHUNK(i, ev)                                                                      \
+  do {                                                                                               \
+    if (blockIdx.x == 0 && (i) >= 8 && (i) < 24) g_trace_chunks[((i) - 8) * 16 + (ev)] = clock64(); \
+  } while (0)
 #define ATTN_TRACE(role, i, ev)                                                     \
   do {                                                                              \
     if (blockIdx.x == 0 && (i) >= 8 && (i) < 24) g_trace[((role) * 16 + (i) - 8) * 8 + (ev)] = clock64(); \
   } while (0)
 #else
 #define ATTN_TRACE(role, i, ev) do {} while (0)
+#define ATTN_TRACE_CHUNK(i, ev) do {} while (0)
 #endif
 
 __global__ void __launch_bounds__(kThreads, 1) attn_window_kernel(const __grid_constant__ Params p) {
@@ -379,11 +385,15 @@ __global__ void __launch_bounds__(kThreads, 1) attn_window_kernel(const __grid_c
       for (int u = 0; u < 6; u += 2) {
         const int c = cbeg + u;
         tmem_ld_wait();
+        if (tracer && half == 0) ATTN_TRACE_CHUNK(i, 2 * u);
         if (in_range(c + 1)) tmem_ld_32x32(t_lane + kColS + (c + 1) * 32, rb);
         emit(ra, c);
+        if (tracer && half == 0) ATTN_TRACE_CHUNK(i, 2 * u + 1);
         tmem_ld_wait();
+        if (tracer && half == 0) ATTN_TRACE_CHUNK(i, 2 * u + 2);
         if (u + 2 < 6 && in_range(c + 2)) tmem_ld_32x32(t_lane + kColS + (c + 2) * 32, ra);
         emit(rb, c + 1);
+        if (tracer && half == 0) ATTN_TRACE_CHUNK(i, 2 * u + 3);
         // release slabs of S: half 0 owns chunks 0-5 (slab 0, first half of slab 1), half 1 6-11
         if ((half == 0 && u == 2) || (half == 1 && u == 0) || u == 4) {
           const int slab = (half == 0) ? (u == 2 ? 0 : 1) : (u == 0 ? 1 : 2);
@@ -460,6 +470,9 @@ __global__ void __launch_bounds__(kThreads, 1) attn_window_kernel(const __grid_c
 #ifdef OSUDIT_ATTN_TRACE
 extern "C" int osudit_debug_attn_trace(long long* host_out) {
   return cudaMemcpyFromSymbol(host_out, attn_tc::g_trace, sizeof(attn_tc::g_trace)) == cudaSuccess ? 0 : -1;
+}
+extern "C" int osudit_debug_attn_trace_chunks(long long* host_out) {
+  return cudaMemcpyFromSymbol(host_out, attn_tc::g_trace_chunks, sizeof(attn_tc::g_trace_chunks)) == cudaSuccess ? 0 : -1;
 }
 #endif
 

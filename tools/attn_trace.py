@@ -35,3 +35,12 @@ for i in range(2, 7):
     print(f"--- tile {8 + i} (period vs previous tile: {tr[0, i, 0] - tr[0, i - 1, 0]} cycles)")
     for role in range(3):
         print("   " + "  ".join(f"{names[role][e]}={tr[role, i, e] - tr[0, i, 0]}" for e in range(8) if names[role][e]))
+if hasattr(lib, "osudit_debug_attn_trace_chunks"):
+    b2 = np.zeros(16 * 16, dtype=np.int64)
+    lib.osudit_debug_attn_trace_chunks.argtypes = [ctypes.c_void_p]
+    assert lib.osudit_debug_attn_trace_chunks(b2.ctypes.data) == 0
+    ch = b2.reshape(16, 16)
+    for i in range(2, 5):
+        e = ch[i]
+        print(f"tile {8 + i}, half 0 / quadrant 0 chunks (wait->emit cycles | emit cycles): " + "  ".join(
+            f"c{k}: +{e[2 * k] - (e[2 * k - 1] if k else e[0])} | {e[2 * k + 1] - e[2 * k]}" for k in range(6)))
