@@ -6,17 +6,29 @@ sys.path.insert(0, os.path.join(ROOT, "osu-diffusion_b200"))
 import numpy as np
 import torch
 from osudit import _lib, ops
-M = 262144
 N, K = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (2304, 768)
-epi = ops.EPI_BF16_GELU if len(sys.argv) > 3 and sys.argv[3] == "gelu" else ops.EPI_BF16
+mode = sys.argv[3] if len(sys.argv) > 3 else "plain"
+M = int(sys.argv[4]) if len(sys.argv) > 4 else 262144
+epi = {"plain": ops.EPI_BF16, "gelu": ops.EPI_BF16_GELU, "gelu_save": ops.EPI_BF16_GELU_SAVE, "dgelu": ops.EPI_BF16_DGELU}[mode]
 a = torch.randn(M, K, device="cuda").to(torch.bfloat16)
 w = (torch.randn(N, K, device="cuda") / math.sqrt(K)).to(torch.bfloat16)
 bias = torch.randn(N, device="cuda")
 out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
-for _ in range(3): ops.gemm([a], [w], bias, epi, out)
+aux = torch.randn(M, N, device="cuda").to(torch.bfloat16)
+def run():
+    if mode in ("plain", "gelu"): ops.gemm([a], [w], bias, epi, out)
+    else: ops.gemm_aux(a, w, None if mode == "dgelu" else bias, epi, out, aux)
+for _ in range(3): run()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(10): run()
+e1.record(); torch.cuda.synchronize()
+print(f"{mode} M={M}: {e0.elapsed_time(e1) / 10 * 1e3:.1f} us  {2 * M * N * K / (e0.elapsed_time(e1) / 10) / 1e9:.0f} TFLOP/s")
 torch.cuda.synchronize()
 buf = np.zeros(2 * 8 * 20, dtype=np.int64)
 lib = _lib.load()
+if not hasattr(lib, "osudit_debug_gemm_trace"):
+    sys.exit(0)
 lib.osudit_debug_gemm_trace.argtypes = [ctypes.c_void_p]
 assert lib.osudit_debug_gemm_trace(buf.ctypes.data) == 0
 tr = buf.reshape(2, 8, 20)
