@@ -28,7 +28,8 @@ int make_tensor_map_2d(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t 
 namespace g2 {
 
 constexpr int BM = 128;        // rows per CTA (256 per pair)
-constexpr int BN = 256;        // columns per pair; each CTA stages BN/2 rows of B
+// BN (template parameter): columns per pair, 256 or — for widths that 256 does not divide, DiT-XL's 1152 / 3456 and
+// DiT-S's 384 / 1152 — 192; each CTA stages BN/2 rows of B.
 constexpr int BK = 64;
 #ifndef OSUDIT_GELU_FP32  // the forward GELU epilogue works on half2 pairs unless this is defined (see gelu_tanh_pair)
 #define OSUDIT_GELU_H2 1
@@ -44,12 +45,16 @@ constexpr int BK = 64;
 constexpr int kEpiGroups = OSUDIT_G2_EPI_GROUPS;
 constexpr int kStages = kEpiGroups == 1 ? 6 : 5;
 constexpr int kBytesA = BM * BK * 2;
-constexpr int kBytesB = (BN / 2) * BK * 2;
-constexpr int kStageBytes = kBytesA + kBytesB;  // 32 KB per CTA
 constexpr int kStagingBytes = BM * 128;
 constexpr int kThreads = 64 + 256 * kEpiGroups;
-constexpr int kBiasBytes = kEpiGroups * 2 * BN * 4;  // bias slice of the current / next tile, per epilogue group
-constexpr int kSmemBytes = kStages * kStageBytes + 2 * kEpiGroups * kStagingBytes + 1024 + kBiasBytes;
+template <int BN>
+struct Cfg {
+  static_assert(BN == 256 || BN == 192, "UMMA N of the pair");
+  static constexpr int kBytesB = (BN / 2) * BK * 2;
+  static constexpr int kStageBytes = kBytesA + kBytesB;  // 32 KB (28 KB) per CTA, a multiple of the 1 KB swizzle atom
+  static constexpr int kBiasBytes = kEpiGroups * 2 * BN * 4;  // bias slice of the current / next tile, per epilogue group
+  static constexpr int kSmemBytes = kStages * kStageBytes + 2 * kEpiGroups * kStagingBytes + 1024 + kBiasBytes;
+};
 
 struct Params {
   CUtensorMap tma_a, tma_b, tma_out, tma_aux;
@@ -164,9 +169,10 @@ __device__ long long g_gemm_trace[2 * 8 * 20];
 #define GEMM_TRACE(role, it, ev) do {} while (0)
 #endif
 
-template <int EPI>
+template <int EPI, int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm2_kernel(const __grid_constant__ Params p) {
+  constexpr int kBytesB = Cfg<BN>::kBytesB, kStageBytes = Cfg<BN>::kStageBytes;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* staging = smem + kStages * kStageBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + 2 * kEpiGroups * kStagingBytes);
@@ -227,7 +233,7 @@ gemm2_kernel(const __grid_constant__ Params p) {
   } else if (warp == 1) {
     // -------------------------------------------------------------- MMA issuer (leader only)
     if (leader && lane == 0) {
-      // kind::f16: D fp32, A/B bf16 K-major, N = 256, M = 256 (pair)
+      // kind::f16: D fp32, A/B bf16 K-major, N = BN, M = 256 (pair)
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(BN >> 3) << 17) |
                                  (static_cast<uint32_t>((2 * BM) >> 4) << 24);
       int stage = 0;
@@ -290,7 +296,7 @@ gemm2_kernel(const __grid_constant__ Params p) {
       // this tile's 256 bias values go through shared memory (one global load per thread per tile, issued before
       // the wait for the accumulator) instead of 8 dependent __ldg per thread per chunk on the critical path
       float* s_bias = s_bias_all + (grp * 2 + (it & 1)) * BN;
-      s_bias[ep_tid] = p.bias != nullptr ? __ldg(p.bias + n0 + ep_tid) : 0.f;
+      if (ep_tid < BN) s_bias[ep_tid] = p.bias != nullptr ? __ldg(p.bias + n0 + ep_tid) : 0.f;
       if (ep_tid == 0) GEMM_TRACE(1, it, 0);
       warp_mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
@@ -404,18 +410,19 @@ gemm2_kernel(const __grid_constant__ Params p) {
   }
 }
 
-template <int EPI>
+template <int EPI, int BN>
 static int launch2(const Params& p, cudaStream_t stream) {
+  constexpr int kSmemBytes = Cfg<BN>::kSmemBytes;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm2_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm2_kernel<EPI, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e != cudaSuccess) return set_error(-5, cudaGetErrorString(e));
     configured = true;
   }
   const int tiles = p.m_tiles * p.n_tiles;
   int clusters = num_sms() / 2;
   if (tiles < clusters) clusters = tiles;
-  gemm2_kernel<EPI><<<2 * clusters, kThreads, kSmemBytes, stream>>>(p);
+  gemm2_kernel<EPI, BN><<<2 * clusters, kThreads, kSmemBytes, stream>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(-6, cudaGetErrorString(e));
   return 0;
@@ -430,7 +437,7 @@ extern "C" int osudit_debug_gemm_trace(long long* host_out) {
 #endif
 
 bool gemm_2cta_applicable(int nseg, int64_t M, int64_t N, int epilogue) {
-  return nseg == 1 && epilogue >= g2::EPI_BF16 && epilogue <= g2::EPI_BF16_DGELU && N % 256 == 0 &&
+  return nseg == 1 && epilogue >= g2::EPI_BF16 && epilogue <= g2::EPI_BF16_DGELU && (N % 256 == 0 || N % 192 == 0) &&
          M >= 256 * 37;  // at least half a wave of 256-row tiles, otherwise the 1-CTA kernel balances better
 }
 
@@ -438,6 +445,7 @@ int gemm_2cta_launch(const void* a, int64_t lda, const void* b, int64_t ldb, int
                      const float* bias, int epilogue, void* out, int64_t ldo, void* aux, int64_t ld_aux,
                      cudaStream_t stream) {
   using namespace g2;
+  const int BN = N % 256 == 0 ? 256 : 192;
   Params p;
   p.kblocks = static_cast<int>((K + BK - 1) / BK);
   p.M = static_cast<int>(M);
@@ -462,10 +470,11 @@ int gemm_2cta_launch(const void* a, int64_t lda, const void* b, int64_t ldb, int
     }
   }
   switch (epilogue) {
-    case EPI_BF16: return launch2<EPI_BF16>(p, stream);
-    case EPI_BF16_GELU: return launch2<EPI_BF16_GELU>(p, stream);
-    case EPI_BF16_GELU_SAVE: return launch2<EPI_BF16_GELU_SAVE>(p, stream);
-    default: return launch2<EPI_BF16_DGELU>(p, stream);
+    case EPI_BF16: return BN == 256 ? launch2<EPI_BF16, 256>(p, stream) : launch2<EPI_BF16, 192>(p, stream);
+    case EPI_BF16_GELU: return BN == 256 ? launch2<EPI_BF16_GELU, 256>(p, stream) : launch2<EPI_BF16_GELU, 192>(p, stream);
+    case EPI_BF16_GELU_SAVE:
+      return BN == 256 ? launch2<EPI_BF16_GELU_SAVE, 256>(p, stream) : launch2<EPI_BF16_GELU_SAVE, 192>(p, stream);
+    default: return BN == 256 ? launch2<EPI_BF16_DGELU, 256>(p, stream) : launch2<EPI_BF16_DGELU, 192>(p, stream);
   }
 }
 

@@ -33,6 +33,10 @@ def bf(t):
     (2048, 768, 3072, ops.EPI_BF16),      # fc2 (long K)
     (300 * 7, 1152, 1152, ops.EPI_BF16),  # DiT-XL width, ragged M
     (40000, 768, 768, ops.EPI_BF16),      # > 148 tiles per CTA wave: persistent loop + TMEM double buffer
+    (9600 + 77, 1152, 1152, ops.EPI_BF16),  # CTA-pair kernel at the 192-column tile (DiT-XL out-proj), ragged M
+    (9600, 3456, 1152, ops.EPI_BF16),     # DiT-XL QKV: 18 tiles of 192
+    (10000, 384, 1536, ops.EPI_BF16),     # DiT-S fc2: 2 tiles of 192, long K
+    (9600, 1152, 384, ops.EPI_BF16_GELU),  # 192-column tile with the GELU epilogue
 ])
 def test_gemm_single_segment(M, N, K, epi):
     g = torch.Generator(device=DEV).manual_seed(M + N + K)
@@ -49,7 +53,8 @@ def test_gemm_single_segment(M, N, K, epi):
             ref = torch.nn.functional.gelu(ref, approximate="tanh")
         out = ops.gemm([a], [w], bias, epi, torch.empty(M, N, device=DEV, dtype=torch.bfloat16))
         assert rel(out.float(), ref) < 3e-3          # bf16 output rounding only
-        assert torch.equal(out, bf(ref)) or float((out.float() - ref).abs().max()) < 3e-2
+        # element-wise: bf16 rounding is relative (half an ulp = 2^-9 |ref|), and with 3e7 outputs some reach |ref| > 8
+        assert float(((out.float() - ref).abs() / ref.abs().clamp_min(1.0)).max()) < 6e-3
 
 
 def test_gemm_no_bias_and_garbage_free_tails():

@@ -67,10 +67,10 @@ def test_gelu_forward_backward():
     assert rel(dbias - 1.0, x2.grad.sum(0)) < 2e-3
 
 
-@pytest.mark.parametrize("M", [9700, 300])  # CTA-pair kernel with the fused epilogue / two-launch path
-def test_gemm_with_gelu_save_and_dgelu_epilogues(M):
+@pytest.mark.parametrize("M,N", [(9700, 768), (300, 768), (9700, 1152)])  # CTA-pair kernel with the fused epilogue
+def test_gemm_with_gelu_save_and_dgelu_epilogues(M, N):                    # (256- / 192-column tiles) / two-launch path
     g = torch.Generator(device=DEV).manual_seed(M)
-    N, K = 768, 256
+    K = 256
     a = bf(torch.randn(M, K, device=DEV, generator=g))
     w = bf(torch.randn(N, K, device=DEV, generator=g) / math.sqrt(K))
     bias = torch.randn(N, device=DEV, generator=g)

@@ -49,6 +49,18 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     ms_step = e0.elapsed_time(e1) / (2 * K)
+    if os.environ.get("OSUDIT_KERNEL_TABLE"):  # per-kernel device time of one pass, to stderr
+        from torch.autograd import DeviceType
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            run()
+            torch.cuda.synchronize()
+        ka = [e for e in prof.key_averages() if e.device_type == DeviceType.CUDA]
+        tot = sum(e.device_time_total for e in ka) / K / 1e3
+        print("GPU busy %.2f ms per denoising step" % tot, file=sys.stderr)
+        for e in sorted(ka, key=lambda e: -e.device_time_total)[:16]:
+            print("  %-90s %8.3f ms  x%d  (%.1f%%)" % (e.key[:90], e.device_time_total / K / 1e3, e.count // K,
+                                                      e.device_time_total / K / 10 / tot), file=sys.stderr)
     D, depth, H = m.hidden_size, len(m.blocks), m.num_heads
     pairs = sum(min(T - 1, j + W) - max(0, j - (W - 1)) + 1 for j in range(T))
     flop_step = 2 * n * (T * (24 * D * D * depth + 2 * 528 * D + 8 * D) + pairs * 4 * D * depth)

@@ -2,7 +2,10 @@ import sys, math, torch
 sys.path.insert(0, "/root/repo/osu-diffusion_b200")
 from osudit import ops
 M = 262144
-for (N, K, epi, name) in ((3072, 768, ops.EPI_BF16, "fc1 shape, no GELU"), (3072, 768, ops.EPI_BF16_GELU, "fc1 shape, GELU"),
+SHAPES_XL = ((3456, 1152, ops.EPI_BF16, "XL qkv"), (1152, 1152, ops.EPI_BF16, "XL out-proj"),
+             (4608, 1152, ops.EPI_BF16_GELU, "XL fc1+GELU"), (1152, 4608, ops.EPI_BF16, "XL fc2"),
+             (1152, 384, ops.EPI_BF16, "S qkv"), (384, 1536, ops.EPI_BF16, "S fc2"))
+for (N, K, epi, name) in SHAPES_XL if "xl" in sys.argv[1:] else ((3072, 768, ops.EPI_BF16, "fc1 shape, no GELU"), (3072, 768, ops.EPI_BF16_GELU, "fc1 shape, GELU"),
                           (2304, 768, ops.EPI_BF16, "qkv shape"), (2304, 768, ops.EPI_BF16_GELU, "qkv shape + GELU"),
                           (1536, 768, ops.EPI_BF16, "N=1536"), (4608, 768, ops.EPI_BF16, "N=4608")):
     a = torch.randn(M, K, device="cuda").to(torch.bfloat16)
