@@ -1,8 +1,8 @@
 // 2-CTA (cta_group::2) variant of the bf16 GEMM for the four large per-block contractions
 // (models.py:164-170 QKV / out-proj, models.py:112-119 fc1+GELU / fc2).
 //
-// A CTA pair (one TPC) computes a 256 x 256 output tile with UMMA M=256, N=256: each CTA stages its
-// own 128 rows of A and its own 128 rows (N half) of B, so per MMA every SM reads 8 KB of shared
+// A CTA pair (one TPC) computes a 256 x BN output tile with UMMA M=256, N=BN (256, or 192 where 256 does not divide
+// the width): each CTA stages its own 128 rows of A and its own BN/2 rows (N half) of B, so per MMA every SM reads 8 KB of shared
 // memory instead of 12 KB and TMA writes 32 KB instead of 48 KB per k-block — the 1-CTA kernel's
 // K=768 shapes sit at ~70 % tensor-pipe activity because of exactly that traffic (profiles/r01).
 //
