@@ -350,7 +350,11 @@ def test_cuda_graph_training_step_matches_eager(monkeypatch):
         assert abs(out[True][0] - out[False][0]) < 1e-5 * abs(out[False][0]), (step, out[True][0], out[False][0])
         worst = max((rel(out[True][1][k], out[False][1][k]), k) for k in out[False][1])
         print(f"step {step}: loss {out[True][0]:.6f}, worst graph-vs-eager gradient rel-L2 {worst[0]:.2e} ({worst[1]})")
-        assert worst[0] < 5e-4, (step, worst)  # only atomic / reduce-add ordering (and bf16 re-rounding of it) differs
+        # Only atomic / reduce-add ordering differs — ~1e-7, except when that noise flips the bf16 rounding of one of the
+        # 4 x 384 conditioning-path gradients that feed a weight-gradient GEMM: one flip of a large element is 2^-8 of
+        # it, i.e. 1e-4..6e-4 of the whole t_embedder gradient at this batch size (seen in ~1 of 6 comparisons).  A stale
+        # weight copy or a clobbered activation would show up as O(0.1).
+        assert worst[0] < 2e-3, (step, worst)
     assert len(set(round(v, 5) for v in losses)) == 4
     assert len(otrain._train_graphs) == 1
     # two forwards in flight: the second must not overwrite the first one's saved activations
@@ -364,7 +368,7 @@ def test_cuda_graph_training_step_matches_eager(monkeypatch):
     m_g.zero_grad(set_to_none=True)
     monkeypatch.setattr(otrain, "_GRAPHS_ENABLED", False)
     d.training_losses(m_g, x.to(DEV), t.to(DEV), kw, noise=noise.to(DEV))["loss"].mean().backward()
-    assert max(rel(g1[k], p.grad) for k, p in m_g.named_parameters() if p.grad is not None) < 1e-3
+    assert max(rel(g1[k], p.grad) for k, p in m_g.named_parameters() if p.grad is not None) < 2e-3
     otrain._train_graphs.clear()
 
 
