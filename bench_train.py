@@ -29,7 +29,7 @@ SEQ = 128
 
 
 def flops_per_seq(model_name):
-    D, depth, H = {"DiT-S": (384, 12, 6), "DiT-B": (768, 12, 12), "DiT-L": (1024, 24, 16)}[model_name]
+    D, depth, H = {"DiT-S": (384, 12, 6), "DiT-B": (768, 12, 12), "DiT-L": (1024, 24, 16), "DiT-XL": (1152, 28, 16)}[model_name]
     gemm_tok = 24 * D * D * depth + 2 * 528 * D + 2 * D * 4
     attn = SEQ * SEQ * 4 * D * depth
     return 3 * (SEQ * gemm_tok + attn)
