@@ -142,3 +142,55 @@ def test_synthetic_inputs_shape_and_layout():
     assert bool((c[:, 128:].sum(1) == 1).all())  # one-hot datapoint type
     (x, o2, c2), y2 = synth.training_batch(4, 128, seed=0)
     assert x.shape == (4, 2, 128) and float(x.min()) >= 0 and float(x.max()) <= 1 and y2.shape == (4,)
+
+
+def _spacing_digest(fn, n, spec):
+    import zlib
+    try:
+        kept = sorted(fn(n, spec))
+    except Exception as e:
+        return type(e).__name__
+    return "%d:%08x" % (len(kept), zlib.crc32(",".join(map(str, kept)).encode()))
+
+
+def test_space_timesteps_sweep_matches_reference(golden_dir):
+    """Every single count and every "ddimN" over 1000 / 250 / 37 steps plus multi-section lists (2 613 specs), kept
+    steps bit-exact and the same exception type where the reference raises (tests/golden/make_golden_spacing.py)."""
+    from diffusion import space_timesteps
+    from oracle.diffusion import spaced_steps
+    want = {k: v for k, v in json.load(open(os.path.join(golden_dir, "spacing.json"))).items()
+            if not k.startswith("betas|")}
+    assert len(want) == 2613
+    bad = []
+    for key, digest in want.items():
+        n, spec = key.split("|")
+        if _spacing_digest(space_timesteps, int(n), spec) != digest:
+            bad.append(("product", key))
+        if not spec.startswith("ddim") and _spacing_digest(spaced_steps, int(n), spec) != digest:
+            bad.append(("oracle", key))
+    assert not bad, bad[:10]
+
+
+def test_named_beta_schedules_bit_exact(golden_dir):
+    """`get_named_beta_schedule` for both schedules at eight lengths: float64 bytes identical to the reference's, and
+    the same exception for an unknown name (gaussian_diffusion.py:112-134); the oracle's two builders likewise."""
+    import zlib
+    from diffusion import get_named_beta_schedule
+    from oracle import diffusion as odiff
+    want = {k: v for k, v in json.load(open(os.path.join(golden_dir, "spacing.json"))).items() if k.startswith("betas|")}
+    assert len(want) == 24
+
+    def digest(fn, *a):
+        try:
+            b = np.asarray(fn(*a))
+        except Exception as e:
+            return type(e).__name__
+        return "%d:%08x" % (len(b), zlib.crc32(b.astype("<f8").tobytes()))
+
+    for key, d in want.items():
+        _, name, n = key.split("|")
+        assert digest(get_named_beta_schedule, name, int(n)) == d, key
+        if name == "linear":
+            assert digest(odiff.linear_betas, int(n)) == d, ("oracle", key)
+        elif name == "squaredcos_cap_v2":
+            assert digest(odiff.cosine_betas, int(n)) == d, ("oracle", key)
