@@ -194,3 +194,16 @@ def test_named_beta_schedules_bit_exact(golden_dir):
             assert digest(odiff.linear_betas, int(n)) == d, ("oracle", key)
         elif name == "squaredcos_cap_v2":
             assert digest(odiff.cosine_betas, int(n)) == d, ("oracle", key)
+
+
+def test_positional_embedding_module_matches_reference(golden_dir):
+    """The host-side drop-in `positional_embedding` (data preparation callers, data_loading.py:161) against outputs
+    of the reference's module on the same inputs: even / odd / tiny dims, a non-default max_period, sequence forms."""
+    import positional_embedding as pe
+    z = np.load(os.path.join(golden_dir, "posemb.npz"))
+    t, o, p = (torch.from_numpy(z[k]) for k in ("t", "o", "p"))
+    for dim in (256, 128, 9, 2):
+        np.testing.assert_array_equal(pe.timestep_embedding(t, dim).numpy(), z[f"timestep_{dim}"])
+    np.testing.assert_array_equal(pe.timestep_embedding(t, 128, max_period=100).numpy(), z["timestep_128_mp100"])
+    np.testing.assert_array_equal(pe.offset_sequence_embedding(o / 10, 128).numpy(), z["offset_128"])
+    np.testing.assert_array_equal(pe.position_sequence_embedding(p, 128).numpy(), z["position_128"])
