@@ -207,3 +207,19 @@ def test_positional_embedding_module_matches_reference(golden_dir):
     np.testing.assert_array_equal(pe.timestep_embedding(t, 128, max_period=100).numpy(), z["timestep_128_mp100"])
     np.testing.assert_array_equal(pe.offset_sequence_embedding(o / 10, 128).numpy(), z["offset_128"])
     np.testing.assert_array_equal(pe.position_sequence_embedding(p, 128).numpy(), z["position_128"])
+
+
+def test_label_dropout_matches_reference(golden_dir):
+    """models.py:56-67: the null class replaces a label where `rand(B) < p` on the global generator (same draws as the
+    reference under the same seed) or where `force_drop_ids == 1`; the table has one extra row only when p > 0."""
+    import models
+    g = json.load(open(os.path.join(golden_dir, "labels.json")))
+    labels, force = torch.tensor(g["labels"]), torch.tensor(g["force"])
+    for case in g["cases"]:
+        emb = models._LabelEmbedder(52670, 8, case["p"])
+        assert emb.embedding_table.weight.shape[0] == case["table_rows"]
+        torch.manual_seed(5)
+        assert emb.token_drop(labels).tolist() == case["first"]
+        assert emb.token_drop(labels).tolist() == case["second"]
+        assert emb.token_drop(labels, force_drop_ids=force).tolist() == case["forced"]
+    assert models._LabelEmbedder(52670, 8, 0.0).embedding_table.weight.shape[0] == g["table_rows_without_dropout"]
