@@ -33,6 +33,9 @@ class _Attention(_Holder):
         self.in_proj_weight = nn.Parameter(torch.empty(3 * hidden, hidden))
         self.in_proj_bias = nn.Parameter(torch.zeros(3 * hidden))
         self.out_proj = nn.Linear(hidden, hidden, bias=True)
+        # drawn here, after out_proj's own constructor draws, as nn.MultiheadAttention does: the global generator
+        # is consumed in the reference's order, so a seeded construction yields the reference's initial weights
+        nn.init.xavier_uniform_(self.in_proj_weight)
 
 
 class _Mlp(_Holder):  # models.py:83-119
@@ -121,15 +124,15 @@ class DiT(nn.Module):
 
     def initialize_weights(self):
         """Same distributions as models.py:275-304 (xavier-uniform Linears with zero bias,
-        N(0, 0.02) embedders, zeros for every adaLN modulation and the output projection)."""
+        N(0, 0.02) embedders, zeros for every adaLN modulation and the output projection), drawn in the same
+        order: together with the constructors above, `torch.manual_seed(s); DiT_models[name](...)` gives
+        bit-identical weights to the reference's (tests/golden/init_digest.json).  The packed in-projection keeps
+        the xavier draw of its constructor, as in the reference (it is not an nn.Linear)."""
         for m in self.modules():
             if isinstance(m, nn.Linear):
                 nn.init.xavier_uniform_(m.weight)
                 if m.bias is not None:
                     nn.init.zeros_(m.bias)
-            elif isinstance(m, _Attention):
-                nn.init.xavier_uniform_(m.in_proj_weight)
-                nn.init.zeros_(m.in_proj_bias)
         nn.init.normal_(self.xoc_embedder.mlp[0].weight, std=0.02)
         nn.init.normal_(self.y_embedder.embedding_table.weight, std=0.02)
         nn.init.normal_(self.t_embedder.mlp[0].weight, std=0.02)

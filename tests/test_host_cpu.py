@@ -223,3 +223,19 @@ def test_label_dropout_matches_reference(golden_dir):
         assert emb.token_drop(labels).tolist() == case["second"]
         assert emb.token_drop(labels, force_drop_ids=force).tolist() == case["forced"]
     assert models._LabelEmbedder(52670, 8, 0.0).embedding_table.weight.shape[0] == g["table_rows_without_dropout"]
+
+
+def test_seeded_construction_gives_the_reference_weights(golden_dir):
+    """`torch.manual_seed(s); DiT_models[name](**kw)` consumes the global generator in the reference's order
+    (models.py:243-304 and the constructors it calls): every initial tensor is bit-identical to the reference's,
+    and so is the generator state afterwards (tests/golden/make_golden_init.py)."""
+    import zlib
+    import models
+    for case in json.load(open(os.path.join(golden_dir, "init_digest.json"))):
+        torch.manual_seed(case["seed"])
+        m = models.DiT_models[case["name"]](**case["kwargs"])
+        assert torch.rand(4).tolist() == case["next_rand"]
+        sd = m.state_dict()
+        assert list(sd) == list(case["crc"])
+        bad = [k for k, v in sd.items() if "%08x" % zlib.crc32(v.contiguous().numpy().tobytes()) != case["crc"][k]]
+        assert not bad, (case["name"], bad[:6])
