@@ -25,7 +25,7 @@ extern "C" {
 
 #define OSUDIT_VERSION 2
 
-int osudit_version(void);
+int osudit_version(void); /* library ABI version (no reference counterpart: the reference has no FFI) */
 const char* osudit_last_error(void);
 
 /* Epilogues of osudit_gemm_bf16. */
@@ -64,25 +64,29 @@ int osudit_attn_band(const void* qkv, void* out, int B, int T, int H, int head_d
  * operands transposed by osudit_transpose_bf16.
  * ---------------------------------------------------------------------------------------------- */
 
-/* Weight gradient of y = x W^T: out[M,N] (fp32, ACCUMULATED: zero it first) += dy[rows,M]^T . x[rows,N],
+/* Weight gradient of y = x W^T — autograd of every nn.Linear on the path (models.py:35-38,112-119,152-159,164-170,193,
+ * 233-234) under loss.backward() (train.py:257): out[M,N] (fp32, ACCUMULATED: zero it first) += dy[rows,M]^T . x[rows,N],
  * both operands read token-major as MN-major tcgen05 operands; the token dimension is split across
  * CTAs and combined with TMA reduce-add.  ld_* in elements (multiples of 8). */
 int osudit_gemm_wgrad(const void* dy, int64_t ld_dy, const void* x, int64_t ld_x, int64_t rows, int64_t M,
                       int64_t N, float* out, int64_t ldo, void* stream);
 
-/* dqkv (bf16 [B*T, 3*H*hd]) from dout (bf16 [B*T, H*hd]), the forward's qkv / out / lse.
+/* Autograd of nn.MultiheadAttention under the band / generic mask (models.py:130-135,164-170; train.py:257):
+ * dqkv (bf16 [B*T, 3*H*hd]) from dout (bf16 [B*T, H*hd]), the forward's qkv / out / lse.
  * delta is fp32 [B, H, T] scratch.  Band semantics as in osudit_attn_band; head_dim 64 or 72.
  * dbias_qkv (fp32 [3*H*hd], ACCUMULATED, may be NULL) += column sums of dqkv: the in_proj_bias gradient. */
 int osudit_attn_band_bwd(const void* qkv, const void* out, const void* dout, const float* lse,
                          float* delta, void* dqkv, int B, int T, int H, int head_dim, int w_left,
                          int w_right, float* dbias_qkv, void* stream);
 
-/* out[cols, out_ld] (bf16, out_ld >= rows: pad the GEMM K dimension to a multiple of 8) = in[rows, cols]^T;
+/* Operand re-layout for the data-gradient GEMMs (dx = dy W, i.e. autograd of F.linear, models.py:112-119,164-170):
+ * out[cols, out_ld] (bf16, out_ld >= rows: pad the GEMM K dimension to a multiple of 8) = in[rows, cols]^T;
  * in is bf16, or fp32 when in_is_f32. */
 int osudit_transpose_bf16(const void* in, void* out, int64_t rows, int64_t cols, int64_t out_ld, int in_is_f32,
                           void* stream);
 
-/* backward == 0: out = gelu_tanh(pre);  backward == 1: out = dy * gelu_tanh'(pre).  bf16, n % 8 == 0. */
+/* nn.GELU(approximate="tanh") of the Mlp and its derivative (models.py:112-119):
+ * backward == 0: out = gelu_tanh(pre);  backward == 1: out = dy * gelu_tanh'(pre).  bf16, n % 8 == 0. */
 int osudit_gelu(const void* pre, const void* dy, void* out, int64_t n, int backward, void* stream);
 
 /* Single-segment bf16 GEMM (as osudit_gemm_bf16) whose epilogue also touches a second bf16 [M, N] tensor `aux`:
@@ -96,11 +100,13 @@ int osudit_gemm_bf16_aux(const void* a, int64_t lda, const void* b, int64_t ldb,
                          const float* bias, int epilogue, void* out, int64_t ldo, void* aux, int64_t ld_aux,
                          void* stream);
 
-/* out[rows, N] = dy * gelu_tanh'(pre) and dbias[N] (fp32, ACCUMULATED, may be NULL) += column sums of out:
+/* Backward through the Mlp's GELU (models.py:112-119), for shapes the fused DGELU epilogue does not take:
+ * out[rows, N] = dy * gelu_tanh'(pre) and dbias[N] (fp32, ACCUMULATED, may be NULL) += column sums of out:
  * the fc1 pre-activation gradient together with the fc1 bias gradient.  bf16, N % 8 == 0. */
 int osudit_gelu_bwd(const void* pre, const void* dy, void* out, int64_t rows, int N, float* dbias, void* stream);
 
-/* out[N] (fp32, ACCUMULATED: caller zeroes) += column sums of in[rows, N] (bf16 or fp32): bias grads. */
+/* out[N] (fp32, ACCUMULATED: caller zeroes) += column sums of in[rows, N] (bf16 or fp32): the bias gradients of the
+ * nn.Linear layers (models.py:35-38,112-119,152-159,164-170,193,233-234). */
 int osudit_colsum(const void* in, int in_is_f32, int64_t rows, int N, float* out, void* stream);
 
 /* Backward of x_out = x + gate[b] * y (models.py:161-163,172):
@@ -171,7 +177,8 @@ int osudit_timestep_features(const int64_t* t, const float* freqs128, int rows, 
 int osudit_silu_split(const float* a, const int32_t* a_index, const float* table, const int64_t* y,
                       int64_t rows, int D, void* hi, void* lo, void* stream);
 
-/* fp32 -> split-bf16 (lo may be NULL): packs nn.Linear weights for the GEMM. */
+/* fp32 -> split-bf16 (lo may be NULL): packs nn.Linear weights for the GEMM (the reference keeps fp32 parameters and
+ * casts per call under autocast, train.py:249-255; sample.py runs them in fp32). */
 int osudit_split_bf16(const float* a, int64_t n, void* hi, void* lo, void* stream);
 
 /* One reverse-diffusion update, optionally with the classifier-free-guidance combine.
@@ -204,7 +211,8 @@ int osudit_diffusion_loss(const float* model_out, const float* x0, const float* 
                           const int64_t* t, const float* coef_table, int B, int T, int use_l1,
                           float* term_main, float* term_vb, float* dmodel_out, void* stream);
 
-/* out[b, :] = in[b, :] * g[b] (chain rule through the per-sample loss). */
+/* out[b, :] = in[b, :] * g[b]: chain rule from `loss = terms["loss"].mean()` (train.py:255-257) through the per-sample
+ * terms of training_losses (gaussian_diffusion.py:785-874). */
 int osudit_scale_rows(const float* in, const float* g, int B, int64_t per_row, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
@@ -232,11 +240,12 @@ typedef struct OsuditOptSeg {
   long long n;    /* elements                                                   */
 } OsuditOptSeg;
 
-/* Elements per chunk: chunk c = (segment index, chunk offset within the segment) covers elements
+/* (train.py:154,258-261.)  Elements per chunk: chunk c = (segment index, chunk offset within the segment) covers elements
  * [offset * E, min((offset + 1) * E, n)). */
 int osudit_opt_chunk_elems(void);
 
-/* segs: DEVICE array of OsuditOptSeg; chunks: DEVICE array of nchunks (int32 segment, int32 offset) pairs.
+/* torch.optim.AdamW.step + update_ema (train.py:36-45,154,258-261) in one launch.
+ * segs: DEVICE array of OsuditOptSeg; chunks: DEVICE array of nchunks (int32 segment, int32 offset) pairs.
  * step (device fp32 scalar) is incremented first unless *found_inf != 0; then, unless *found_inf != 0, every
  * element gets torch.optim.AdamW's update with g / *grad_scale and ema = ema*ema_decay + p_new*(1-ema_decay).
  * grad_scale / found_inf may be NULL (no scaling / never skip). */
@@ -251,7 +260,8 @@ int osudit_adamw_ema_step(const void* segs, const int32_t* chunks, int nchunks, 
  * K-segments of osudit_gemm_bf16 (widths 3K, 2K, K) accumulate the six significant products.
  * ---------------------------------------------------------------------------------------------- */
 
-/* osudit_gemm_bf16 with EPI_F32 and "precise" accumulation: the tensor core adds into its fp32 accumulator
+/* fp32-mode form of every nn.Linear forward (models.py:35-38,112-119,152-159,164-170,193,233-234):
+ * osudit_gemm_bf16 with EPI_F32 and "precise" accumulation: the tensor core adds into its fp32 accumulator
  * with truncation, a bias that grows with the length of the accumulation chain (measured 4e-6 relative at
  * 200 MMAs).  Here the concatenated K range of all segments is cut into chains of kb_per_split 64-wide
  * k-blocks; each chain's partial tile is added into `out` (zeroed by this call) with round-to-nearest fp32
@@ -276,12 +286,14 @@ int osudit_final_layer_f32(float* x, const float* branch, const float* gate, con
                            const float* scale, int64_t mod_ld, int64_t rows, int T, int D, const float* w,
                            const float* bias, int out_channels, float* out, void* stream);
 
-/* osudit_attn_band on fp32 qkv [B*T, 3*H*head_dim] -> fp32 out [B*T, H*head_dim], computed in fp32 on the
+/* fp32-mode attention (models.py:164-170 with the mask of sample.py:81-84):
+ * osudit_attn_band on fp32 qkv [B*T, 3*H*head_dim] -> fp32 out [B*T, H*head_dim], computed in fp32 on the
  * CUDA cores (head_dim 64 or 72; band, full (w = -1) or generic mask as osudit_attn_band). */
 int osudit_attn_band_f32(const float* qkv, float* out, int B, int T, int H, int head_dim, int w_left,
                          int w_right, const uint8_t* mask, void* stream);
 
-/* osudit_embed_xoc / osudit_timestep_features writing the fp32 feature rows unsplit:
+/* fp32-mode feature builders (models.py:227-233, 35-36; positional_embedding.py:29-77):
+ * osudit_embed_xoc / osudit_timestep_features writing the fp32 feature rows unsplit:
  * a fp32 [B*T, 384 + E]; out fp32 [rows, 256]. */
 int osudit_embed_xoc_f32(const float* x, const float* o, const float* c, const float* freqs64, float pf_x,
                          float pf_y, int B, int xrows, int T, int E, float* a, void* stream);
