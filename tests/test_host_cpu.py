@@ -239,3 +239,31 @@ def test_seeded_construction_gives_the_reference_weights(golden_dir):
         assert list(sd) == list(case["crc"])
         bad = [k for k, v in sd.items() if "%08x" % zlib.crc32(v.contiguous().numpy().tobytes()) != case["crc"][k]]
         assert not bad, (case["name"], bad[:6])
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver times next to the GPU arm) needs no GPU and prints one
+    JSON line with the GPU arm's metric / unit / config keys plus `impl`, `cpu_baseline` and a zero-copy `e2e`."""
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"].startswith("beatmaps/sec") and d["unit"] == "beatmaps/s"
+    assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1 and d["value"] > 0
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
+    assert d["config"]["workload"].startswith("DiT-B sampling")
+
+
+def test_bench_reference_arm_other_ranks_exit_quietly():
+    """Under torchrun (N > 1) only rank 0 runs the CPU arm; every other rank exits 0 without output or work."""
+    import subprocess
+    import sys
+    env = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT="29533")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
+                        "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
+    assert r.returncode == 0 and r.stdout.strip() == ""
