@@ -267,3 +267,17 @@ def test_bench_reference_arm_other_ranks_exit_quietly():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
                         "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_missing_library_fails_loudly():
+    """Without libosudit.so the product path raises on first use (no CPU / PyTorch fallback): checked in a fresh
+    interpreter with OSUDIT_LIB pointing at a file that does not exist."""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from osudit import _lib\n"
+            "try:\n    _lib.load()\nexcept _lib.OsuditError as e:\n    print('RAISED', 'no CPU' in str(e))\n"
+            "else:\n    print('LOADED')\n") % os.path.join(ROOT, "osu-diffusion_b200")
+    env = dict(os.environ, OSUDIT_LIB="/nonexistent/libosudit.so")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env)
+    assert r.stdout.strip() == "RAISED True", (r.stdout, r.stderr[-500:])
