@@ -184,3 +184,15 @@ def test_feature_builder_oracle_matches_reference_golden(golden_dir):
     # synthetic inputs used by the benches are built the same way
     xs, os_, cs = synth.beatmap_features(64, seed=5)
     assert cs.shape == (144, 64) and float(os_[0]) == 0.0 and float(xs.max()) <= 1.0
+
+
+def test_diffusion_utils_restatement_covers_every_branch(golden_dir):
+    """oracle._normal_kl / _std_normal_cdf / _disc_gauss_loglik against the reference's diffusion_utils on a grid that
+    reaches the edge bins (x < -0.999, x > 0.999), the 1e-12 clamp and extreme log-variances
+    (tests/golden/make_golden_utils.py)."""
+    z = {k: torch.from_numpy(v) for k, v in np.load(os.path.join(golden_dir, "diffusion_utils.npz")).items()}
+    torch.testing.assert_close(odiff._disc_gauss_loglik(z["x"], z["mean"], z["log_scale"]), z["loglik"],
+                               rtol=2e-6, atol=1e-6)
+    torch.testing.assert_close(odiff._normal_kl(z["m1"], z["lv1"], z["m2"], z["lv2"]), z["kl"], rtol=2e-6, atol=1e-6)
+    torch.testing.assert_close(odiff._std_normal_cdf(z["z"]), z["cdf"], rtol=2e-6, atol=1e-7)
+    assert float(z["loglik"].min()) < -27 and float(z["loglik"].max()) == 0.0  # clamp and saturated bins are in the grid
