@@ -9,9 +9,14 @@ sampling of 64 synthetic 2048-datapoint beatmaps (128 model rows) through the pu
 N>1 (launched by torchrun) shards independent beatmaps over ranks with no collective on the data
 path (weak scaling: 64 beatmaps per GPU); timing is CUDA events, max over ranks.
 
-`--impl reference` times the reference algorithm's CPU port (oracle/, torch fp32 on all host
-threads; the reference itself is Python and absent on the GPU box) on a bounded sample of the same
-workload.  Prints exactly one JSON line on rank 0.
+The same JSON line carries BASELINE.json's second metric under "train": sequences/sec of DiT-B seq-len-128
+training at global batch 256 (config 3), data-parallel over the N ranks with the NCCL gradient all-reduce of
+train.py:152,257 (strong scaling: 256 / N sequences per GPU), timed in the same process after the sampling arm.
+
+`--impl reference` times the reference's own CPU path on a bounded sample of the same workload: the UNMODIFIED
+reference modules when `baseline/_ref/` (written by `__graft_entry__.build()` from /root/reference; git-ignored,
+travels to the GPU box) or $OSU_DIFFUSION_REF holds them (`kind: "reference"`), else the oracle port (`kind: "port"`).
+Prints exactly one JSON line on rank 0.
 """
 import argparse
 import json
@@ -31,8 +36,32 @@ import torch  # noqa: E402
 
 MODEL, N_BEATMAPS, SEQ, STEPS_DIFF, CFG, BAND = "DiT-B", 64, 2048, 100, 1.5, 128
 METRIC = "beatmaps/sec DiT-B 100-step CFG sampling"
-NCU_GEMM_TRAFFIC_GB = 1.57  # ncu --set full, profiles/r01d_summary.md: (1.560 + 0.765 + 1.963 + 2.011) / 4
 UNIT = "beatmaps/s"
+TRAIN_MODEL, TRAIN_SEQ, TRAIN_GLOBAL_BATCH = "DiT-B", 128, 256  # BASELINE config 3
+
+
+def ncu_gemm_traffic():
+    """(GB per launch, source) of the dominant GEMM's DRAM traffic: mean over the `gemm2_kernel` rows of the newest
+    committed `--set full` summary under profiles/ (dram bytes_read + bytes_write columns), None when absent."""
+    import glob
+    import re
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_summary.md")), reverse=True):
+        rd = wr = None
+        vals = []
+        for line in open(path):
+            cells = [c.strip() for c in line.strip().strip("|").split("|")]
+            if "dram bytes_read [Gbyte]" in line and "kernel" in cells[0]:
+                rd = next(i for i, c in enumerate(cells) if c.startswith("dram bytes_read"))
+                wr = next(i for i, c in enumerate(cells) if c.startswith("dram bytes_write"))
+                continue
+            if rd is not None and re.match(r"`gemm2_kernel<", cells[0]) and len(cells) > max(rd, wr):
+                try:
+                    vals.append(float(cells[rd]) + float(cells[wr]))
+                except ValueError:
+                    pass
+        if vals:
+            return round(sum(vals) / len(vals), 3), f"{os.path.relpath(path, ROOT)} ({len(vals)} gemm2_kernel launches)"
+    return None, "no ncu --set full summary under profiles/"
 
 
 def workload_config(n_gpus):
@@ -183,6 +212,12 @@ def run_native(args, rank, world, local_rank):
 
     total = N_BEATMAPS * world * args.steps
     value = total / (ms / 1e3)
+    train = None
+    if not args.no_train:
+        model._engine = None  # drop the sampling workspaces (5.6 GB) before the training arm allocates its own
+        del model, zd, od, cd, yd
+        torch.cuda.empty_cache()
+        train = run_train(rank, world, local_rank, dist, device)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -198,11 +233,145 @@ def run_native(args, rank, world, local_rank):
         "gpu_launches": launches,
         "model_tflops": round(flops_per_beatmap() * value / world / 1e12, 1),
         "roofline": roof,
+        "train": train,
     }
-    line["cpu_baseline"] = cpu_baseline_sample(sample_steps=1) if world == 1 else None
+    line["cpu_baseline"] = cpu_baseline_sample() if world == 1 else None
     if dist is not None:
         dist.destroy_process_group()
     return line
+
+
+
+# ------------------------------------------------------------------------- training arm
+def train_flops_per_seq():
+    """fwd + bwd (3x forward) algorithmic flops of one training sequence, full attention over the window."""
+    D, depth = 768, 12
+    gemm_tok = 24 * D * D * depth + 2 * 528 * D + 2 * D * 4
+    return 3 * (TRAIN_SEQ * gemm_tok + TRAIN_SEQ * TRAIN_SEQ * 4 * D * depth)
+
+
+def run_train(rank, world, local_rank, dist, device, steps=20, warmup=8):
+    """BASELINE config 3 through the drop-in API: train.py:243-261's step (label dropout, t ~ U{0..999},
+    `training_losses` under fp16 autocast, GradScaler, AdamW 1e-4, EMA 0.9999) on synthetic windows, DDP over the
+    ranks.  Two variants are timed: "stock" = train.py's own optimizer / EMA loop / DistributedDataParallel call,
+    and the headline = the documented opt-ins (osudit.optim.FusedAdamWEMA, osudit.ddp.wrap: bf16 buckets, bucket
+    views, SMs reserved for NCCL).  `allreduce_ms_exposed` = step time minus the same step under `no_sync()`."""
+    import contextlib
+    from copy import deepcopy
+    import models
+    from diffusion import create_diffusion
+    from osudit import ddp, ops, synth, train as otrain
+    from osudit.optim import FusedAdamWEMA
+
+    B = TRAIN_GLOBAL_BATCH // world
+    diffusion = create_diffusion("", noise_schedule="squaredcos_cap_v2", use_l1=True)
+    (x, o, c), y = synth.training_batch(B, TRAIN_SEQ, seed=rank)
+    host = [t.pin_memory() for t in (x, o, c, y)]
+
+    def build(fused):
+        torch.manual_seed(0)
+        m = models.DiT_models[TRAIN_MODEL](num_classes=52670, context_size=144, class_dropout_prob=0.2)
+        g = torch.Generator().manual_seed(1)
+        with torch.no_grad():  # non-zero adaLN / output layers so every gradient is exercised
+            for k, v in m.state_dict().items():
+                if "adaLN_modulation" in k or k.startswith("final_layer.linear"):
+                    v.copy_(torch.randn(v.shape, generator=g) * 0.02)
+        m = m.to(device).train()
+        ema = deepcopy(m).requires_grad_(False)
+        net = m
+        if world > 1:
+            if fused:
+                net = ddp.wrap(m, device_ids=[local_rank])
+            else:
+                ddp.set_sm_limit(0)
+                net = torch.nn.parallel.DistributedDataParallel(m, device_ids=[local_rank])  # train.py:152
+        if fused:
+            opt = FusedAdamWEMA(net.parameters(), lr=1e-4, weight_decay=0)
+            opt.attach_ema(ema, m, decay=0.9999)
+        else:
+            opt = torch.optim.AdamW(net.parameters(), lr=1e-4, weight_decay=0)
+        return m, ema, net, opt
+
+    def measure(fused):
+        m, ema, net, opt = build(fused)
+        scaler = torch.amp.GradScaler("cuda")
+
+        def step(sync=True):
+            xd, od, cd, yd = [t.to(device, non_blocking=True) for t in host]
+            t = torch.randint(0, diffusion.num_timesteps, (B,), device=device)
+            ctx = contextlib.nullcontext() if (sync or world == 1) else net.no_sync()
+            with ctx:
+                with torch.autocast(device_type="cuda", dtype=torch.float16):
+                    loss = diffusion.training_losses(net, xd, t, dict(o=od, c=cd, y=yd))["loss"].mean()
+                scaler.scale(loss).backward()
+            scaler.step(opt)
+            scaler.update()
+            opt.zero_grad(set_to_none=True)
+            if not fused:
+                with torch.no_grad():  # update_ema, train.py:36-45
+                    for pe, pm in zip(ema.parameters(), m.parameters()):
+                        pe.mul_(0.9999).add_(pm.detach(), alpha=1 - 0.9999)
+            return loss
+
+        def timed(k, sync=True):
+            if dist is not None:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(k):
+                loss = step(sync)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            if dist is not None:
+                tt = torch.tensor([ms], device=device)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                ms = float(tt.item())
+            return ms / k, float(loss.detach())
+
+        for _ in range(warmup):
+            step()
+        l0 = ops.launch_count
+        ms, loss = timed(steps)
+        launches = ops.launch_count - l0
+        ms_nosync = timed(max(steps // 2, 4), sync=False)[0] if world > 1 else ms
+        nparam = sum(p.numel() for p in m.parameters() if p.requires_grad)
+        del net, opt, ema, m
+        otrain.release_graphs()
+        ddp.set_sm_limit(0)
+        torch.cuda.empty_cache()
+        return ms, ms_nosync, loss, launches, nparam
+
+    ms_f, ns_f, loss_f, launches, nparam = measure(True)
+    ms_s, ns_s, loss_s, _, _ = measure(False)
+    pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    tf_peak = json.load(open(pk_path))["bf16_tflops_sustained"] if os.path.exists(pk_path) else 1400.0
+    value = TRAIN_GLOBAL_BATCH / (ms_f / 1e3)
+    tfl = train_flops_per_seq() * value / world / 1e12
+    bytes_ar = nparam * 2
+    return {
+        "metric": f"train seq/s {TRAIN_MODEL} seq-len {TRAIN_SEQ}", "value": round(value, 1), "unit": "seq/s",
+        "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": round(ms_f, 3), "scaling": "strong",
+        "global_batch": TRAIN_GLOBAL_BATCH, "per_gpu_batch": B, "dtype": "bf16", "data": "synthetic",
+        "final_loss": round(loss_f, 4), "gpu_launches": launches,
+        "config": {"workload": f"{TRAIN_MODEL} training, seq-len {TRAIN_SEQ}, global batch {TRAIN_GLOBAL_BATCH}, L1+VB loss, "
+                               "AdamW 1e-4, EMA, fp16-autocast context + GradScaler as train.py:243-261",
+                   "optimizer": "osudit.optim.FusedAdamWEMA (opt-in: AdamW + EMA + unscale in one launch)",
+                   "parallelism": f"dp{world}: DistributedDataParallel over NCCL via osudit.ddp.wrap (bf16 gradient buckets, "
+                                  "bucket views, 16 SMs reserved for NCCL)" if world > 1 else "dp1 (no collective)"},
+        "allreduce_ms_exposed": round(ms_f - ns_f, 3) if world > 1 else 0.0,
+        "collective": None if world == 1 else {
+            "op": "NCCL all-reduce of the parameter gradients (train.py:152,257), the only collective on the path",
+            "bytes_per_step": bytes_ar, "dtype": "bf16 buckets",
+            "floor_ms_at_725GBs_busbw": round(bytes_ar * 2 * (world - 1) / world / 725e9 * 1e3, 3)},
+        "roofline": {"bound": "tensor", "achieved": round(tfl, 1), "peak": tf_peak, "unit": "TFLOP/s (model-level, per GPU)",
+                     "frac": round(tfl / tf_peak, 4)},
+        "stock": {"value": round(TRAIN_GLOBAL_BATCH / (ms_s / 1e3), 1), "ms_per_step": round(ms_s, 3),
+                  "allreduce_ms_exposed": round(ms_s - ns_s, 3) if world > 1 else 0.0, "final_loss": round(loss_s, 4),
+                  "what": "train.py unchanged: torch.optim.AdamW + update_ema loop + stock DistributedDataParallel "
+                          "(fp32 buckets)"},
+    }
 
 
 def kernel_roofline(model, diffusion, zd, od, cd, yd, mask_d, device):
@@ -266,11 +435,16 @@ def kernel_roofline(model, diffusion, zd, od, cd, yd, mask_d, device):
     af, ams, an = agg(rec["attn"])
     step_ms = sum(e0.elapsed_time(e1) for k in rec for e0, e1, _ in rec[k])
     ach = fl / (ms / 1e3) / 1e12
+    traffic, traffic_src = ncu_gemm_traffic()
+    # algorithmic bytes of one launch: A read + W read + out written, bf16 (mean over the timed block GEMMs)
+    shapes = [tag for _, _, (w, tag) in rec["gemm"] if big(tag)]
+    algo_gb = sum(2.0 * (m * k + nn * k + m * nn) for m, nn, k in shapes) / max(len(shapes), 1) / 1e9
     return {"bound": "tensor", "kernel": "g2::gemm2_kernel (cta_group::2 tcgen05 GEMM: QKV, out-proj, fc1+GELU, fc2 "
             "launches)",
             "achieved": round(ach, 1), "peak": tf_peak, "unit": "TFLOP/s", "frac": round(ach / tf_peak, 4),
-            "traffic": NCU_GEMM_TRAFFIC_GB, "traffic_unit": "GB per launch (dram read+write, mean of the QKV/out-proj/"
-            "fc1/fc2 launches in profiles/r01d_summary.md; algorithmic 1.56)", "peak_source": src, "launches_timed": n,
+            "traffic": traffic, "traffic_unit": f"GB per launch (ncu dram read+write, mean over {traffic_src}); "
+            f"algorithmic {round(algo_gb, 2)}", "peak_source": src,
+            "launches_timed": n,
             "avg_launch_ms": round(ms / max(n, 1), 4), "share_of_step": round(ms / step_ms, 3),
             "per_shape_tflops": {k: round(v[0] / (v[1] / 1e3) / 1e12, 1) for k, v in by_shape.items()},
             "hbm_kernel": {"kernel": "ln_modulate_kernel", "bound": "hbm",
@@ -282,61 +456,188 @@ def kernel_roofline(model, diffusion, zd, od, cd, yd, mask_d, device):
 
 
 # ------------------------------------------------------------------------ CPU reference arm
-def cpu_denoise_step_seconds(n, T, repeats):
-    """Time `repeats` CFG denoising steps of the oracle port (fp32, all host threads)."""
-    from oracle import diffusion as odiff
-    from oracle import dit as odit
-    from osudit import synth
-    shape = odit.shape_of(MODEL)
-    sd = odit.init_state_dict(shape, seed=1)
-    z, o, c, y = synth.sampling_batch(n, T, seed=0)
-    mask = synth.band_mask(T, BAND)
-    s = odiff.Schedule(str(STEPS_DIFF))
-    g = torch.Generator().manual_seed(0)
-    x, times = z, []
-    with torch.no_grad():
-        for r in range(repeats):
-            i = STEPS_DIFF - 1 - r
-            t = torch.full((2 * n,), i)
-            t0 = time.perf_counter()
-            out = odit.forward_with_cfg(sd, shape.heads, x, odiff.original_timesteps(s, t), o, c, y, CFG, mask)
-            x = odiff.p_sample(s, out, x, t, torch.randn(x.shape, generator=g))["sample"]
-            times.append(time.perf_counter() - t0)
-    return times
+def reference_root():
+    """Directory holding the UNMODIFIED reference modules (models.py, positional_embedding.py, diffusion/), or None."""
+    for cand in (os.environ.get("OSU_DIFFUSION_REF"), os.path.join(ROOT, "baseline", "_ref"), "/root/reference"):
+        if cand and os.path.exists(os.path.join(cand, "models.py")) and \
+                os.path.exists(os.path.join(cand, "diffusion", "gaussian_diffusion.py")):
+            return cand
+    return None
 
 
-def cpu_baseline_sample(sample_steps=1):
-    torch.set_num_threads(os.cpu_count() or 1)
-    cpu_denoise_step_seconds(1, SEQ, 1)  # warm-up (allocator, thread pool)
-    ts = cpu_denoise_step_seconds(1, SEQ, sample_steps)
-    per_step = sum(ts) / len(ts)
-    return {"value": round(1.0 / (per_step * STEPS_DIFF), 6), "unit": UNIT, "cores": torch.get_num_threads(),
-            "kind": "port",
-            "sample": f"oracle/ (torch fp32 CPU restatement of the reference) on 1 beatmap (2 CFG rows) x {SEQ} "
-                      f"datapoints, {sample_steps} of {STEPS_DIFF} denoising steps timed after 1 warm-up step, "
-                      f"extrapolated linearly to {STEPS_DIFF} steps"}
+def _load_synth():
+    """osudit/synth.py by file path: the reference arm must not put this repo's drop-in `models` / `diffusion` on
+    sys.path next to the reference's modules of the same names."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("osudit_synth", os.path.join(PKG, "osudit", "synth.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+class ReferenceCPU:
+    """sample.py:69-108,174-182 and train.py:243-261 restated around the unmodified reference modules on the host
+    cores (fp32, all threads): the scripts themselves need `slider` / matplotlib / CUDA and cannot be launched."""
+    kind = "reference"
+
+    def __init__(self, root):
+        for q in (PKG, ROOT):
+            while q in sys.path:
+                sys.path.remove(q)
+        sys.path.insert(0, root)
+        os.environ.setdefault("PYTHONDONTWRITEBYTECODE", "1")
+        sys.dont_write_bytecode = True
+        import models as ref_models  # noqa: the reference's own module
+        from diffusion import create_diffusion as ref_create
+        self.models, self.create = ref_models, ref_create
+        self.synth = _load_synth()
+        self.where = root
+
+    def _model(self, name, dropout):
+        torch.manual_seed(1)
+        m = self.models.DiT_models[name](num_classes=52670, context_size=144, class_dropout_prob=dropout)
+        g = torch.Generator().manual_seed(1)
+        with torch.no_grad():
+            for k, v in m.state_dict().items():
+                if "adaLN_modulation" in k or k.startswith("final_layer.linear"):
+                    v.copy_(torch.randn(v.shape, generator=g) * 0.02)
+        return m
+
+    def denoise_step_seconds(self, n, T, repeats):
+        if getattr(self, "_sampler", None) is None:  # built once: the timed region is sample.py's loop body only
+            self._sampler = (self._model(MODEL, 0.1).eval(), self.create(str(STEPS_DIFF), noise_schedule="squaredcos_cap_v2"))
+        m, d = self._sampler
+        z, o, c, y = self.synth.sampling_batch(n, T, seed=0)
+        mask = self.synth.band_mask(T, BAND)
+        x, times = z, []
+        with torch.no_grad():
+            for r in range(repeats):
+                t = torch.full((2 * n,), STEPS_DIFF - 1 - r)
+                t0 = time.perf_counter()
+                x = d.p_sample(m.forward_with_cfg, x, t, clip_denoised=True,
+                               model_kwargs=dict(o=o, c=c, y=y, cfg_scale=CFG, attn_mask=mask))["sample"]
+                times.append(time.perf_counter() - t0)
+        return times
+
+    def train_seq_per_s(self, B=8, steps=2):
+        m = self._model(TRAIN_MODEL, 0.2).train()
+        opt = torch.optim.AdamW(m.parameters(), lr=1e-4, weight_decay=0)
+        d = self.create("", noise_schedule="squaredcos_cap_v2", use_l1=True)
+        (x, o, c), y = self.synth.training_batch(B, TRAIN_SEQ, seed=0)
+
+        def step():
+            t = torch.randint(0, d.num_timesteps, (B,))
+            loss = d.training_losses(m, x, t, dict(o=o, c=c, y=y))["loss"].mean()
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+
+        step()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        return B * steps / (time.perf_counter() - t0), B
+
+
+class PortCPU:
+    """Fallback when the reference modules are not on this machine: the oracle's torch-CPU restatement."""
+    kind = "port"
+    where = "oracle/"
+
+    def denoise_step_seconds(self, n, T, repeats):
+        from oracle import diffusion as odiff
+        from oracle import dit as odit
+        from osudit import synth
+        shape = odit.shape_of(MODEL)
+        if getattr(self, "_sd", None) is None:
+            self._sd = odit.init_state_dict(shape, seed=1)
+        sd = self._sd
+        z, o, c, y = synth.sampling_batch(n, T, seed=0)
+        mask = synth.band_mask(T, BAND)
+        s = odiff.Schedule(str(STEPS_DIFF))
+        g = torch.Generator().manual_seed(0)
+        x, times = z, []
+        with torch.no_grad():
+            for r in range(repeats):
+                i = STEPS_DIFF - 1 - r
+                t = torch.full((2 * n,), i)
+                t0 = time.perf_counter()
+                out = odit.forward_with_cfg(sd, shape.heads, x, odiff.original_timesteps(s, t), o, c, y, CFG, mask)
+                x = odiff.p_sample(s, out, x, t, torch.randn(x.shape, generator=g))["sample"]
+                times.append(time.perf_counter() - t0)
+        return times
+
+    def train_seq_per_s(self, B=8, steps=2):
+        from oracle import diffusion as odiff, dit as odit
+        from osudit import synth
+        shape = odit.shape_of(TRAIN_MODEL)
+        sd = odit.init_state_dict(shape, seed=1)
+        params = {k: v.requires_grad_(v.is_floating_point() and "playfield" not in k) for k, v in sd.items()}
+        opt = torch.optim.AdamW([p for p in params.values() if p.requires_grad], lr=1e-4, weight_decay=0)
+        s = odiff.Schedule("")
+        (x, o, c), y = synth.training_batch(B, TRAIN_SEQ, seed=0)
+
+        def step():
+            t = torch.randint(0, 1000, (B,))
+            loss = odiff.training_losses(s, lambda xt, tt: odit.forward(params, shape.heads, xt, tt, o, c, y),
+                                         x, t, torch.randn_like(x), use_l1=True)["loss"].mean()
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+
+        step()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        return B * steps / (time.perf_counter() - t0), B
+
+
+def cpu_arm():
+    root = None if os.environ.get("OSUDIT_BENCH_CPU_ARM") == "port" else reference_root()
+    return ReferenceCPU(root) if root else PortCPU()
+
+
+def cpu_baseline_sample():
+    """The reference arm on a bounded sample, in its own process (the reference's module names collide with the
+    drop-in's): 1 warm-up + 1 timed denoising step of one beatmap; returns its `cpu_baseline` object."""
+    try:
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1",
+                              "--warmup", "1"], capture_output=True, text=True, timeout=900, cwd=ROOT,
+                             env={k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")})
+        line = json.loads(out.stdout.strip().splitlines()[-1])
+        cb = line["cpu_baseline"]
+        cb["train"] = line.get("train")
+        return cb
+    except Exception as e:  # the baseline is a reported number, never a reason to lose the GPU measurement
+        return {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "unavailable", "sample": f"failed: {e}"}
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return None
     torch.set_num_threads(os.cpu_count() or 1)
-    for _ in range(args.warmup):
-        cpu_denoise_step_seconds(1, SEQ, 1)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        cpu_denoise_step_seconds(1, SEQ, 1)
-    per_sample = (time.perf_counter() - t0) / args.steps  # one denoising step of one beatmap
-    value = 1.0 / (per_sample * STEPS_DIFF)
-    sample = (f"each bench step = 1 of {STEPS_DIFF} denoising steps of 1 beatmap (2 CFG rows) x {SEQ} datapoints "
-              f"on the oracle port, extrapolated linearly to the full {STEPS_DIFF}-step sampling")
+    arm = cpu_arm()
+    arm.denoise_step_seconds(1, SEQ, max(args.warmup, 1))
+    ts = arm.denoise_step_seconds(1, SEQ, args.steps)  # each bench step = one denoising step of one beatmap
+    per_step = per_sample = sum(ts) / len(ts)
+    value = 1.0 / (per_step * STEPS_DIFF)
+    train_v, train_b = arm.train_seq_per_s()
+    what = "the unmodified reference modules (" + arm.where + ")" if arm.kind == "reference" else \
+        "oracle/ (torch fp32 CPU restatement of the reference)"
+    sample = (f"{what}: sample.py's p_sample(model.forward_with_cfg, ...) call on 1 beatmap (2 CFG rows) x {SEQ} "
+              f"datapoints, fp32, {torch.get_num_threads()} threads; each bench step = 1 of the {STEPS_DIFF} denoising steps "
+              f"({args.steps} timed after {max(args.warmup, 1)} warm-up), extrapolated linearly to the full sampling")
     return {"impl": "reference", "metric": METRIC, "value": round(value, 6), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(per_sample * 1e3, 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(world),
             "cpu_baseline": {"value": round(value, 6), "unit": UNIT, "cores": torch.get_num_threads(),
-                             "kind": "port", "sample": sample},
+                             "kind": arm.kind, "sample": sample},
             "e2e": {"value": round(value, 6), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "train": {"metric": f"train seq/s {TRAIN_MODEL} seq-len {TRAIN_SEQ}", "value": round(train_v, 2),
+                      "unit": "seq/s", "kind": arm.kind,
+                      "sample": f"train.py:243-261's step (training_losses -> backward -> AdamW) in fp32 on the host "
+                                f"cores, batch {train_b}, 2 steps timed after 1 warm-up"},
             "gpu_launches": 0}
 
 
@@ -346,6 +647,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--no-train", action="store_true", help="skip the training arm (the \"train\" record)")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: keep the real stdout aside and point fd 1 at stderr, so that anything a
     # library writes to C stdout (NCCL prints its version banner there when NCCL_DEBUG is set) cannot precede it

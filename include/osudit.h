@@ -26,6 +26,12 @@ extern "C" {
 #define OSUDIT_VERSION 2
 
 int osudit_version(void); /* library ABI version (no reference counterpart: the reference has no FFI) */
+
+/* Caps the grid of every persistent kernel (GEMMs, windowed attention) at `n` CTAs instead of one per SM (0 = no cap;
+ * rounded down to an even number for the CTA-pair GEMM); returns the previous cap.  Data-parallel training sets it so
+ * that NCCL's all-reduce kernels (train.py:152,257) find free SMs next to the backward instead of queueing behind a
+ * full-machine persistent grid.  Process-wide; takes effect at the next launch (captured graphs keep their grids). */
+int osudit_set_sm_limit(int n);
 const char* osudit_last_error(void);
 
 /* Epilogues of osudit_gemm_bf16. */
@@ -176,6 +182,11 @@ int osudit_timestep_features(const int64_t* t, const float* freqs128, int rows, 
  * front of every adaLN Linear (models.py:73,320,148,189). */
 int osudit_silu_split(const float* a, const int32_t* a_index, const float* table, const int64_t* y,
                       int64_t rows, int D, void* hi, void* lo, void* stream);
+
+/* Device-side assertion that every class label lies in [0, table_rows): the launch traps (as the reference's CUDA
+ * embedding lookup asserts, models.py:73) instead of gathering / scattering outside the table.  Issued in front of
+ * every launch that indexes the embedding table with `y`. */
+int osudit_check_labels(const int64_t* y, int64_t n, int64_t table_rows, void* stream);
 
 /* fp32 -> split-bf16 (lo may be NULL): packs nn.Linear weights for the GEMM (the reference keeps fp32 parameters and
  * casts per call under autocast, train.py:249-255; sample.py runs them in fp32). */

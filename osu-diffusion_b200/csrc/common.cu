@@ -14,7 +14,9 @@ int set_error(int code, const char* msg) {
   return code;
 }
 
-int num_sms() {
+static int g_sm_limit = 0;  // 0 = none; set by osudit_set_sm_limit
+
+static int device_sms() {
   static int cached[64] = {0};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -27,7 +29,18 @@ int num_sms() {
   return cached[dev];
 }
 
+int num_sms() {
+  const int n = device_sms();
+  return (g_sm_limit > 0 && g_sm_limit < n) ? g_sm_limit : n;
+}
+
 }  // namespace osudit
 
 extern "C" const char* osudit_last_error(void) { return osudit::g_err; }
 extern "C" int osudit_version(void) { return OSUDIT_VERSION; }
+extern "C" int osudit_set_sm_limit(int n) {
+  if (n < 0) return osudit::set_error(-1, "set_sm_limit: negative limit");
+  const int prev = osudit::g_sm_limit;
+  osudit::g_sm_limit = n & ~1;  // CTA pairs: keep it even
+  return prev;
+}

@@ -14,6 +14,7 @@
 // these small but precision-critical products at ~fp32 accuracy.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <stdio.h>
 #include <stdint.h>
 
 #include "common.h"
@@ -122,6 +123,17 @@ __global__ void silu_split_kernel(const float* __restrict__ a, const int32_t* __
   split_store(hi, lo, idx, silu(v));
 }
 
+// Device-side assertion on the class labels (what the reference's embedding lookup does on CUDA, models.py:73):
+// a label outside [0, table_rows) stops the launch instead of reading / scattering outside the table.
+__global__ void check_labels_kernel(const int64_t* __restrict__ y, int64_t n, int64_t table_rows) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n && (y[i] < 0 || y[i] >= table_rows)) {
+    printf("osudit: class label %lld at row %lld is outside the embedding table [0, %lld)\n",
+           static_cast<long long>(y[i]), static_cast<long long>(i), static_cast<long long>(table_rows));
+    __trap();
+  }
+}
+
 // fp32 -> split-bf16 (weights are packed once per parameter version with this).
 __global__ void split_kernel(const float* __restrict__ a, int64_t n, __nv_bfloat16* __restrict__ hi,
                              __nv_bfloat16* __restrict__ lo) {
@@ -186,6 +198,14 @@ extern "C" int osudit_silu_split(const float* a, const int32_t* a_index, const f
                       static_cast<cudaStream_t>(stream)>>>(
       a, a_index, table, y, rows, D, static_cast<__nv_bfloat16*>(hi),
       static_cast<__nv_bfloat16*>(lo));
+  OSUDIT_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int osudit_check_labels(const int64_t* y, int64_t n, int64_t table_rows, void* stream) {
+  if (n <= 0 || table_rows <= 0 || y == nullptr) return set_error(-1, "check_labels: bad arguments");
+  check_labels_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      y, n, table_rows);
   OSUDIT_CHECK_LAUNCH();
   return 0;
 }

@@ -437,8 +437,12 @@ extern "C" int osudit_debug_gemm_trace(long long* host_out) {
 #endif
 
 bool gemm_2cta_applicable(int nseg, int64_t M, int64_t N, int epilogue) {
-  return nseg == 1 && epilogue >= g2::EPI_BF16 && epilogue <= g2::EPI_BF16_DGELU && (N % 256 == 0 || N % 192 == 0) &&
-         M >= 256 * 37;  // at least half a wave of 256-row tiles, otherwise the 1-CTA kernel balances better
+  if (!(nseg == 1 && epilogue >= g2::EPI_BF16 && epilogue <= g2::EPI_BF16_DGELU && (N % 256 == 0 || N % 192 == 0)))
+    return false;
+  // at least half a wave of 256-row output tiles over the 74 CTA pairs, otherwise the 1-CTA kernel balances better
+  // (a strong-scaling training rank has M = 4096 rows: 16 row panels x 3..12 column tiles)
+  const int64_t tiles = ((M + 255) / 256) * (N % 256 == 0 ? N / 256 : N / 192);
+  return M >= 256 && tiles >= 37;
 }
 
 int gemm_2cta_launch(const void* a, int64_t lda, const void* b, int64_t ldb, int64_t K, int64_t M, int64_t N,

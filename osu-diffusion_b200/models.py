@@ -15,7 +15,7 @@ import torch
 import torch.nn as nn
 
 from osudit import ops
-from osudit.engine import DiTEngine
+from osudit.engine import DiTEngine, check_inputs
 
 
 class _Holder(nn.Module):
@@ -103,6 +103,10 @@ class DiT(nn.Module):
         if in_channels != 2 or not learn_sigma:
             raise NotImplementedError("the native path covers in_channels=2, learn_sigma=True "
                                       "(the only configuration the reference scripts build)")
+        kin = in_channels * 128 + 128 + context_size  # first-layer input width (models.py:216-219)
+        if kin % 8 != 0:
+            raise ValueError(f"context_size={context_size} gives a first-layer width of {kin}; the native GEMM needs a "
+                             "multiple of 8 (16-byte bf16 rows for TMA); the reference scripts use 144 (sample.py:71)")
         self.learn_sigma = learn_sigma
         self.in_channels = in_channels
         self.context_size = context_size
@@ -167,6 +171,7 @@ class DiT(nn.Module):
             if not v.is_cuda:
                 raise RuntimeError(f"DiT.forward: `{name}` is on {v.device}; the native path runs on "
                                    "CUDA only and has no CPU fallback")
+        check_inputs(self, x, t, o, c, y, x_rows)
         return self.engine().forward(x.float().contiguous(), t.long().contiguous(),
                                      o.float().contiguous(), c.float().contiguous(),
                                      self._labels(y.long()).contiguous(), attn_mask, x_rows)
@@ -187,6 +192,7 @@ class DiT(nn.Module):
                 if not v.is_cuda:
                     raise RuntimeError(f"DiT.forward: `{name}` is on {v.device}; the native path runs "
                                        "on CUDA only and has no CPU fallback")
+            check_inputs(self, x, t, o, c, y)
             if self._train_weights is None:
                 self._train_weights = TrainWeights()
             tw = self._train_weights  # re-packed inside the head node (eagerly, or as part of the CUDA graph)

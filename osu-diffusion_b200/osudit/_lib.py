@@ -21,6 +21,7 @@ _F = c_float
 SIGNATURES = {
     "osudit_version": [],
     "osudit_last_error": [],
+    "osudit_set_sm_limit": [_I],
     "osudit_gemm_bf16": [_I, _P, _P, _P, _P, _P, _L, _L, _P, _I, _P, _L, _P],
     "osudit_attn_band": [_P, _P, _I, _I, _I, _I, _I, _I, _P, _I, _P, _P],
     "osudit_gemm_wgrad": [_P, _L, _P, _L, _L, _L, _L, _P, _L, _P],
@@ -42,6 +43,7 @@ SIGNATURES = {
     "osudit_timestep_features": [_P, _P, _I, _P, _P, _P],
     "osudit_silu_split": [_P, _P, _P, _P, _L, _I, _P, _P, _P],
     "osudit_split_bf16": [_P, _L, _P, _P, _P],
+    "osudit_check_labels": [_P, _L, _L, _P],
     "osudit_diffusion_step": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _I, _I, _P, _P, _P, _P, _P],
     "osudit_cfg_combine": [_P, _I, _I, _F, _P, _P],
     "osudit_q_sample": [_P, _P, _P, _P, _P, _I, _L, _P, _P],

@@ -33,20 +33,22 @@ class MaskSpec:
         self.w_left, self.w_right, self.generic = w_left, w_right, generic
 
 
-_mask_cache: dict = {}
+_mask_cache: dict = {}  # key -> (MaskSpec, the mask tensor): the entry keeps the tensor (and so its address) alive
+_MASK_CACHE_ENTRIES = 16
 
 
 def classify_mask(attn_mask, T: int) -> MaskSpec:
     """sample.py:81-84 builds a (T,T) bool band (True = blocked).  Recognise the closed form once
-    per mask tensor so attention can skip whole key tiles; anything else is applied element-wise."""
+    per mask tensor so attention can skip whole key tiles; anything else is applied element-wise.
+    The classification reads the mask back once (a host sync); later calls with the same tensor are sync-free."""
     if attn_mask is None:
         return MaskSpec()
     if attn_mask.dtype != torch.bool or attn_mask.shape != (T, T):
         raise ValueError("attn_mask must be a (T, T) bool tensor (True = not allowed) or None")
     key = (attn_mask.data_ptr(), attn_mask._version, T, str(attn_mask.device))
-    spec = _mask_cache.get(key)
-    if spec is not None:
-        return spec
+    hit = _mask_cache.get(key)
+    if hit is not None and hit[1].untyped_storage().data_ptr() == attn_mask.untyped_storage().data_ptr():
+        return hit[0]
     allowed = ~attn_mask
     wr = int(allowed[0].sum().item()) - 1
     wl = int(allowed[:, 0].sum().item()) - 1
@@ -56,10 +58,48 @@ def classify_mask(attn_mask, T: int) -> MaskSpec:
         spec = MaskSpec(wl, wr)
     else:
         spec = MaskSpec(-1, -1, attn_mask.to(torch.uint8).contiguous())
-    if len(_mask_cache) > 64:
-        _mask_cache.clear()
-    _mask_cache[key] = spec
+    while len(_mask_cache) >= _MASK_CACHE_ENTRIES:  # FIFO; a captured graph keeps its own reference to its spec
+        _mask_cache.pop(next(iter(_mask_cache)))
+    _mask_cache[key] = (spec, attn_mask)  # holding the tensor means its address cannot be recycled under this key
     return spec
+
+
+def check_inputs(model, x, t, o, c, y, x_rows=None):
+    """Shape checks the reference gets for free from its matmuls / embedding lookups (models.py:227-235,306-325):
+    the native kernels take raw pointers, so a mismatch would read or write out of bounds instead of raising."""
+    if o.dim() != 2:
+        raise ValueError(f"DiT.forward: `o` must be (N, T), got {tuple(o.shape)}")
+    B, T = o.shape
+    if tuple(x.shape) != (B, model.in_channels, T):  # with CFG only the first x_rows rows are read, all B are passed
+        raise ValueError(f"DiT.forward: `x` must be ({B}, {model.in_channels}, {T}), got {tuple(x.shape)}")
+    if x_rows is not None and not 0 < x_rows <= B:
+        raise ValueError(f"DiT.forward: x_rows={x_rows} outside (0, {B}]")
+    if tuple(c.shape) != (B, model.context_size, T):
+        raise ValueError(f"DiT.forward: `c` must be ({B}, {model.context_size}, {T}), got {tuple(c.shape)}")
+    if tuple(t.shape) != (B,) or tuple(y.shape) != (B,):
+        raise ValueError(f"DiT.forward: `t` and `y` must be ({B},), got {tuple(t.shape)} and {tuple(y.shape)}")
+    if B * T == 0:
+        raise ValueError("DiT.forward: empty batch")
+
+
+_label_cache: dict = {}  # (ptr, version, n, rows) -> the tensor whose range was already checked on the host
+
+
+def check_label_range(y, table_rows: int, sync: bool):
+    """A label >= table rows is an IndexError in the reference (embedding lookup, models.py:73).  Inference checks it
+    on the host once per label tensor (`sync`); every call also queues the device-side assert in front of the gather
+    (ops.check_labels), which is what protects the training path without a per-step host synchronisation."""
+    if sync:
+        key = (y.data_ptr(), y._version, y.numel(), table_rows)
+        hit = _label_cache.get(key)
+        if hit is None or hit.untyped_storage().data_ptr() != y.untyped_storage().data_ptr():
+            lo, hi = int(y.min()), int(y.max())
+            if lo < 0 or hi >= table_rows:
+                raise IndexError(f"class label out of range: [{lo}, {hi}] outside the embedding table [0, {table_rows})")
+            while len(_label_cache) >= 16:
+                _label_cache.pop(next(iter(_label_cache)))
+            _label_cache[key] = y
+    ops.check_labels(y, table_rows)
 
 
 class PackedWeights:
@@ -158,6 +198,18 @@ class DiTEngine:
             self._ws[key] = ws
         return ws
 
+    def keepalive(self, B: int, T: int, device, attn_mask):
+        """Everything a captured forward of this shape points into (activation workspace, packed weights, frequency
+        tables, the mask's classification): a CUDA graph holds the returned objects so that evicting a workspace or
+        re-packing the weights can never leave it replaying into freed memory."""
+        precision = getattr(self.model, "precision", "bf16")
+        if precision == "fp32":
+            sched = self._fp32
+            return (sched._ws.get((B, T, str(device))), dict(vars(sched.weights)) if sched.weights else None,
+                    dict(self._freqs), classify_mask(attn_mask, T))
+        return (self._ws.get((B, T, str(device))), dict(vars(self.weights)) if self.weights else None,
+                dict(self._freqs), classify_mask(attn_mask, T))
+
     # ------------------------------------------------------------------ forward
     def conditioning(self, ws, t, y, w):
         """mod[B, depth*6D + 2D] = every adaLN Linear applied to SiLU(t_embedder(t) + y_embedder(y))
@@ -167,6 +219,7 @@ class DiTEngine:
         _gemm3(ws["tf_hi"], ws["tf_lo"], w.t0_w, w.t0_b, ws["t1"])
         ops.silu_split(ws["t1"], ws["s_hi"], ws["s_lo"])
         _gemm3(ws["s_hi"], ws["s_lo"], w.t2_w, w.t2_b, ws["temb"])
+        check_label_range(y, w.table.shape[0], sync=not torch.cuda.is_current_stream_capturing())
         ops.silu_split(ws["temb"], ws["c_hi"], ws["c_lo"], table=w.table, y=y)
         _gemm3(ws["c_hi"], ws["c_lo"], w.mod_w, w.mod_b, ws["mod"])
         return ws["mod"]

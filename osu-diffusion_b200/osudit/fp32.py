@@ -14,7 +14,7 @@ import ctypes
 import torch
 
 from . import _lib, ops
-from .engine import FREQ_SEQ, FREQ_T, classify_mask
+from .engine import FREQ_SEQ, FREQ_T, check_label_range, classify_mask
 
 _PTR3 = ctypes.c_void_p * 3
 _LONG3 = ctypes.c_int64 * 3
@@ -204,6 +204,7 @@ class Fp32Schedule:
         timestep_features(t, eng.freqs(FREQ_T // 2, dev), ws["tf"])
         gemm_f32(split3(ws["tf"], ws["tf3"]), w.t0_w, w.t0_b, ws["t1"])
         gemm_f32(split3(ws["t1"], ws["s3"], act=2), w.t2_w, w.t2_b, ws["temb"])
+        check_label_range(y, w.table.shape[0], sync=not torch.cuda.is_current_stream_capturing())
         gemm_f32(split3(ws["temb"], ws["c3"], act=2, table=w.table, y=y), w.mod_w, w.mod_b, ws["mod"])
         mod = ws["mod"]
 

@@ -50,6 +50,9 @@ class StepGraph:
                 self._body()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.set_rng_state(rng, dev)
+        # the captured launches hold raw pointers into the engine's workspace, packed weights and mask copy: keep those
+        # objects alive for as long as this graph can be replayed, whatever the engine's own caches evict
+        self.keep = module.engine().keepalive(self.x.shape[0], self.x.shape[-1], dev, self.mask)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self._body()

@@ -155,6 +155,13 @@ def silu_split(a, hi, lo, a_index=None, table=None, y=None):
         "osudit_silu_split")
 
 
+def check_labels(y, table_rows: int):
+    """Device-side assert that every label indexes the embedding table (the launch traps otherwise)."""
+    lib = _lib.load()
+    _lib.check(lib.osudit_check_labels(_chk(y, torch.int64, "labels.y"), y.numel(), int(table_rows), _stream()),
+               "osudit_check_labels")
+
+
 def split_bf16(a, need_lo=True):
     a = a.detach().contiguous()
     hi = torch.empty(a.shape, dtype=torch.bfloat16, device=a.device)

@@ -107,7 +107,9 @@ class FusedAdamWEMA(torch.optim.Optimizer):
                     st["step"] = torch.zeros((), dtype=torch.float32, device=dev)
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-            # one device-side step counter per group (torch keeps identical per-parameter copies)
+            # one device-side step counter per group drives the kernel; every parameter's `step` entry aliases it while
+            # training and is cloned per parameter by state_dict() (torch.optim.AdamW keeps one tensor per parameter and
+            # its foreach path would otherwise advance a shared tensor once per parameter after a load)
             step_t = self.state[params[0]]["step"]
             if not (torch.is_tensor(step_t) and step_t.is_cuda and step_t.dtype == torch.float32):
                 step_t = torch.as_tensor(float(step_t), dtype=torch.float32, device=dev)
@@ -133,4 +135,17 @@ class FusedAdamWEMA(torch.optim.Optimizer):
                 float(group["eps"]), float(group["weight_decay"]), self._ema_decay, step_t.data_ptr(),
                 grad_scale.data_ptr() if grad_scale is not None else None,
                 found_inf.data_ptr() if found_inf is not None else None, ops._stream()), "osudit_adamw_ema_step")
+            # the kernel wrote through raw pointers: tell autograd's version counters, which every packed-weight cache
+            # (engine.PackedWeights, fp32.PackedWeightsF32, train.TrainWeights, graphs.StepGraph) keys on
+            touched = list(params)
+            touched += [self._ema[id(p)] for p in params if id(p) in self._ema]
+            torch.autograd.graph.increment_version(touched)
         return loss
+
+    def state_dict(self):
+        """torch.optim.AdamW's layout, with one private `step` tensor per parameter (the live state shares one per
+        group), so the checkpoint loads into the reference's optimizer and back (train.py:287-293)."""
+        sd = super().state_dict()  # its per-parameter dicts ARE the live ones: build new dicts, never edit those
+        sd["state"] = {k: ({**st, "step": st["step"].clone()} if torch.is_tensor(st.get("step")) else dict(st))
+                       for k, st in sd["state"].items()}
+        return sd

@@ -19,7 +19,7 @@ import weakref
 import torch
 
 from . import ops
-from .engine import FREQ_SEQ, FREQ_T, classify_mask
+from .engine import FREQ_SEQ, FREQ_T, check_label_range, classify_mask
 
 
 def _bf(p):
@@ -111,6 +111,7 @@ def forward_train(model, tw: TrainWeights, x, t, o, c, y, attn_mask):
     _gemm3(s1_hi, s1_lo, tw.t2_w, f32(model.t_embedder.mlp[2].bias), temb)
     table = f32(model.y_embedder.embedding_table.weight)
     c_hi, c_lo = _e(B, D, device=dev), _e(B, D, device=dev)
+    check_label_range(y, table.shape[0], sync=False)  # device-side assert only: no host sync on the training path
     ops.silu_split(temb, c_hi, c_lo, table=table, y=y)
     mod = _e(B, (6 * depth + 2) * D, dtype=torch.float32, device=dev)
     _gemm3(c_hi, c_lo, tw.mod_w, tw.mod_b, mod)

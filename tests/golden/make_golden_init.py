@@ -18,7 +18,7 @@ sys.path.insert(0, os.environ.get("OSU_DIFFUSION_REF", "/root/reference"))
 import models  # noqa: E402  (reference)
 
 CASES = [("DiT-S", 0, dict(num_classes=100, context_size=144)),
-         ("DiT-S", 3, dict(num_classes=37, context_size=142, class_dropout_prob=0.0)),
+         ("DiT-S", 3, dict(num_classes=37, context_size=136, class_dropout_prob=0.0)),
          ("DiT-B", 1, dict(num_classes=10, context_size=144, class_dropout_prob=0.2))]
 out = []
 for name, seed, kw in CASES:

@@ -63,8 +63,10 @@ def test_constructor_kwargs_and_init_statistics():
     assert abs(float(sd["xoc_embedder.mlp.0.weight"].std()) - 0.02) < 2e-3
     bound = (6.0 / (128 + 384)) ** 0.5
     assert float(sd["blocks.0.attn.in_proj_weight"].abs().max()) <= bound
-    m2 = models.DiT(hidden_size=128, depth=1, num_heads=2, num_classes=10, class_dropout_prob=0.0)
+    m2 = models.DiT(hidden_size=128, depth=1, num_heads=2, num_classes=10, class_dropout_prob=0.0, context_size=144)
     assert m2.state_dict()["y_embedder.embedding_table.weight"].shape == (10, 128)
+    with pytest.raises(ValueError, match="multiple of 8"):  # the constructor default (142) gives a 526-wide first layer,
+        models.DiT(hidden_size=128, depth=1, num_heads=2, num_classes=10)  # which no TMA row can hold: rejected up front
     import copy
     m3 = copy.deepcopy(m)  # EMA copy (train.py:147)
     assert m3._engine is None and list(m3.state_dict()) == list(sd)
@@ -241,13 +243,16 @@ def test_seeded_construction_gives_the_reference_weights(golden_dir):
         assert not bad, (case["name"], bad[:6])
 
 
-def test_bench_reference_arm_prints_the_contract_line():
+@pytest.mark.parametrize("force_port", [False, True])
+def test_bench_reference_arm_prints_the_contract_line(force_port):
     """`bench.py --impl reference` (the CPU arm the driver times next to the GPU arm) needs no GPU and prints one
-    JSON line with the GPU arm's metric / unit / config keys plus `impl`, `cpu_baseline` and a zero-copy `e2e`."""
+    JSON line with the GPU arm's metric / unit / config keys plus `impl`, `cpu_baseline` and a zero-copy `e2e`.  It runs
+    the unmodified reference modules when they are installed (baseline/_ref, /root/reference), else the oracle port."""
     import subprocess
     import sys
+    env = dict(os.environ, OSUDIT_BENCH_CPU_ARM="port") if force_port else dict(os.environ)
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
-                        "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+                        "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1
@@ -255,7 +260,11 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["impl"] == "reference" and d["metric"].startswith("beatmaps/sec") and d["unit"] == "beatmaps/s"
     assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1 and d["value"] > 0
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
+    have_ref = any(os.path.exists(os.path.join(p, "models.py")) for p in
+                   (os.path.join(ROOT, "baseline", "_ref"), "/root/reference"))
+    want = "port" if (force_port or not have_ref) else "reference"
+    assert d["cpu_baseline"]["kind"] == want and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
+    assert d["train"]["unit"] == "seq/s" and d["train"]["value"] > 0 and d["train"]["kind"] == want
     assert d["config"]["workload"].startswith("DiT-B sampling")
 
 
