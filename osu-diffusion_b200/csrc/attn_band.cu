@@ -610,6 +610,9 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
 bool attn_window_applicable(int T, int head_dim, int w_left, int w_right, const uint8_t* mask);
 int attn_window_launch(const void* qkv, void* out, int B, int T, int H, int w_left, int w_right,
                        cudaStream_t stream);
+bool attn_fa_applicable(int head_dim, const uint8_t* mask);
+int attn_fa_launch(const void* qkv, void* out, int B, int T, int H, int w_left, int w_right, float* lse,
+                   cudaStream_t stream);
 
 }  // namespace osudit
 
@@ -629,6 +632,19 @@ extern "C" int osudit_attn_band(const void* qkv, void* out, int B, int T, int H,
   if (algo == OSUDIT_ATTN_TCGEN05 && !window_ok)
     return set_error(-1, "attn_band: tcgen05 window kernel needs head_dim 64, no generic mask, and "
                          "a band within +-128 or T <= 256");
+  const bool fa_ok = attn_fa_applicable(head_dim, mask);
+  if (algo == OSUDIT_ATTN_FA && !fa_ok)
+    return set_error(-1, "attn_band: the streaming tcgen05 kernel needs head_dim 64 and no generic mask");
+  // AUTO: the streaming two-tile kernel wherever it applies (any T, band or full, with or without lse), except the
+  // long-sequence narrow band of sampling, where the single-pass window kernel is still ~10 % faster (0.73 vs 0.82 ms
+  // per DiT-B layer at 128 x 2048); OSUDIT_ATTN_FA=0 restores the round-1 choice (window kernel / mma.sync)
+  static const bool prefer_fa = [] {
+    const char* e = getenv("OSUDIT_ATTN_FA");
+    return !(e && e[0] == '0');
+  }();
+  const bool long_band = window_ok && T > 256;
+  if (algo == OSUDIT_ATTN_FA || (algo == OSUDIT_ATTN_AUTO && fa_ok && prefer_fa && !long_band))
+    return attn_fa_launch(qkv, out, B, T, H, w_left, w_right, lse, st);
   if (algo != OSUDIT_ATTN_MMA_SYNC && window_ok)
     return attn_window_launch(qkv, out, B, T, H, w_left, w_right, st);
   if (head_dim == 64) return launch_band<64>(qkv, out, B, T, H, w_left, w_right, mask, lse, st);

@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_window_kernel(const __grid_c
     const int half = (warp - 2) >> 2;
     const int row = quad * 32 + lane;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
-    uint8_t* p_row = smem + kSmemP + row * 128;
+    const uint32_t p_row = smem_u32(smem + kSmemP) + row * 128;  // shared-space address of this row of P
     const int swz = row & 7;
     const int cbeg = half * 6;  // this thread's chunks: [cbeg, cbeg + 6)
 
@@ -294,12 +294,11 @@ __global__ void __launch_bounds__(kThreads, 1) attn_window_kernel(const __grid_c
 
       auto store_chunk = [&](int c, const uint32_t(&packed)[16]) {
         // 32 keys = 64 B = four 16-byte chunks of the 128-byte row in K-block c/2
-        uint8_t* blk = p_row + (c >> 1) * kTile;
+        const uint32_t blk = p_row + (c >> 1) * kTile;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int chunk = (c & 1) * 4 + j;
-          *reinterpret_cast<uint4*>(blk + ((chunk ^ swz) << 4)) =
-              make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+          sts128(blk + ((chunk ^ swz) << 4), packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
         }
       };
       // rare: the reference moved up by more than kJump: rescale what this thread already wrote
@@ -307,18 +306,18 @@ __global__ void __launch_bounds__(kThreads, 1) attn_window_kernel(const __grid_c
       // thread's last chunk)
       auto rescale_written = [&](int c_end, float factor) {
         for (int cc = cbeg; cc < c_end; ++cc) {
-          uint8_t* blk = p_row + (cc >> 1) * kTile;
+          const uint32_t blk = p_row + (cc >> 1) * kTile;
           for (int j = 0; j < 4; ++j) {
             const int chunk = (cc & 1) * 4 + j;
-            uint4* ptr = reinterpret_cast<uint4*>(blk + ((chunk ^ swz) << 4));
-            uint4 w = *ptr;
+            const uint32_t addr = blk + ((chunk ^ swz) << 4);
+            uint4 w = lds128(addr);
             uint32_t* e = reinterpret_cast<uint32_t*>(&w);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const float2 f = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&e[k]));
               e[k] = pack_bf16(f.x * factor, f.y * factor);
             }
-            *ptr = w;
+            sts128(addr, w.x, w.y, w.z, w.w);
           }
         }
         sum0 *= factor; sum1 *= factor; sum2 *= factor; sum3 *= factor;

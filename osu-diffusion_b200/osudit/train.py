@@ -132,7 +132,7 @@ def forward_train(model, tw: TrainWeights, x, t, o, c, y, attn_mask):
         ops.gemm([h1], [bw["qkv_w"]], f32(blk.attn.in_proj_bias), ops.EPI_BF16, qkv)
         att = _e(rows, D, device=dev)
         lse = _e(B, H, T, dtype=torch.float32, device=dev)
-        ops.attn_band(qkv, att, B, T, H, hd, spec.w_left, spec.w_right, None, ops.ATTN_MMA_SYNC, lse=lse)
+        ops.attn_band(qkv, att, B, T, H, hd, spec.w_left, spec.w_right, None, ops.ATTN_AUTO, lse=lse)
         y1 = _e(rows, D, device=dev)
         ops.gemm([att], [bw["out_w"]], f32(blk.attn.out_proj.bias), ops.EPI_BF16, y1)
         xb = _e(rows, D, dtype=torch.float32, device=dev)
