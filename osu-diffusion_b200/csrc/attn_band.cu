@@ -610,6 +610,9 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
 bool attn_window_applicable(int T, int head_dim, int w_left, int w_right, const uint8_t* mask);
 int attn_window_launch(const void* qkv, void* out, int B, int T, int H, int w_left, int w_right,
                        cudaStream_t stream);
+bool attn_bwd_tc_applicable(int T, int head_dim);
+int attn_bwd_tc_launch(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int B, int T,
+                       int H, int w_left, int w_right, float* dbias, cudaStream_t stream);
 bool attn_fa_applicable(int head_dim, const uint8_t* mask);
 int attn_fa_launch(const void* qkv, void* out, int B, int T, int H, int w_left, int w_right, float* lse,
                    cudaStream_t stream);
@@ -617,6 +620,8 @@ int attn_fa_launch(const void* qkv, void* out, int B, int T, int H, int w_left, 
 }  // namespace osudit
 
 using namespace osudit;
+
+extern "C" int osudit_colsum(const void* in, int in_is_f32, int64_t rows, int N, float* out, void* stream);
 
 extern "C" int osudit_attn_band(const void* qkv, void* out, int B, int T, int H, int head_dim,
                                 int w_left, int w_right, const uint8_t* mask, int algo, float* lse,
@@ -973,6 +978,13 @@ extern "C" int osudit_attn_band_bwd(const void* qkv, const void* out, const void
   if (w_left < 0 || w_left > T) w_left = T;
   if (w_right < 0 || w_right > T) w_right = T;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  static const bool use_tc = [] {  // OSUDIT_ATTN_BWD_TC=0: the round-1 mma.sync kernels
+    const char* e = getenv("OSUDIT_ATTN_BWD_TC");
+    return !(e && e[0] == '0');
+  }();
+  if (use_tc && attn_bwd_tc_applicable(T, head_dim)) {  // tcgen05: S, dP, dV, dK, dQ in TMEM (attn_bwd_tc.cu)
+    return attn_bwd_tc_launch(qkv, out, dout, lse, dqkv, B, T, H, w_left, w_right, dbias_qkv, st);
+  }
   static const bool use_small = [] {
     const char* e = getenv("OSUDIT_ATTN_BWD_SMALL");
     return !(e && e[0] == '0');
