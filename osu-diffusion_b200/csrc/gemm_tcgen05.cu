@@ -274,7 +274,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
         if (ep_tid == 0) tma_store_wait_read<1>();
         named_bar_sync(1, kEpiThreads);
         const int ncol0 = n0 + c * kEpiCols;
-        uint8_t* my_row = buf + row * 128;
+        const uint32_t my_row = smem_u32(buf) + row * 128;  // shared-space address (generic st would be ST.E)
         uint32_t r[32];
         tmem_ld_32x32(t_row + static_cast<uint32_t>(c * kEpiCols + half * 32), r);
         tmem_ld_wait();
@@ -301,8 +301,8 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
         if (epi_is_f32(EPI)) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {  // 8 x 16 B
-            float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            *reinterpret_cast<float4*>(my_row + ((j ^ (row & 7)) << 4)) = o;
+            sts128(my_row + ((j ^ (row & 7)) << 4), __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
+                   __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
           }
         } else {
 #pragma unroll
@@ -313,7 +313,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
             o.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
             o.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
             const int jj = half * 4 + j;
-            *reinterpret_cast<uint4*>(my_row + ((jj ^ (row & 7)) << 4)) = o;
+            sts128(my_row + ((jj ^ (row & 7)) << 4), o.x, o.y, o.z, o.w);
           }
         }
         fence_proxy_async_smem();

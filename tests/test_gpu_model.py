@@ -222,8 +222,12 @@ def test_free_running_100_steps_damped_fixture(monkeypatch):
     dist = px.pow(2).sum(1).sqrt().flatten()
     print(f"free-running px: median {dist.median():.3f} mean {dist.mean():.3f} max {dist.max():.3f} "
           f"frac>0.5 {float((dist > 0.5).float().mean()):.3f}")
-    assert float(dist.median()) < 0.5
-    assert float((dist > 0.5).float().mean()) < 0.25
+    # bf16 mode, measured: median 0.10, mean 0.16, max 0.90 px, 4.7 % of datapoints beyond 0.5 px; asserted at 1.5x
+    # (the strict "every coordinate within 0.5 px" holds in fp32 mode: tests/test_gpu_parity_full.py)
+    assert float(dist.median()) < 0.15
+    assert float(dist.mean()) < 0.25
+    assert float(dist.max()) < 1.4
+    assert float((dist > 0.5).float().mean()) < 0.08
 
 
 @pytest.mark.parametrize("use_cfg", [True, False])

@@ -116,7 +116,11 @@ def test_fused_optimizer_checkpoint_loads_into_torch_adamw():
         net(x).square().mean().backward()
         fused.step()
         fused.zero_grad(set_to_none=True)
-    sd = fused.state_dict()
+    import io
+    buf = io.BytesIO()
+    torch.save(fused.state_dict(), buf)  # what train.py:287-293 does; a checkpoint shares no storage with the live state
+    buf.seek(0)
+    sd = torch.load(buf, map_location=DEV, weights_only=True)
     steps = [st["step"] for st in sd["state"].values()]
     assert len({s.data_ptr() for s in steps}) == len(steps) and all(float(s) == 3.0 for s in steps)
     twin.load_state_dict(net.state_dict())
@@ -299,18 +303,23 @@ def _script(name):
 
 class _Stubs:
     """Third-party / data-pipeline modules the scripts import but that are outside the hot path (SURVEY §8 out of
-    scope: `slider`, matplotlib, the .osu data loader and exporter), replaced for the duration of one test."""
+    scope: `slider`, matplotlib, the .osu data loader and exporter), replaced for the duration of one test.  The
+    scripts also flip process-wide torch switches at import (TF32 on: train.py:7-8, sample.py:25-26; sample.py:42
+    turns autograd off): restored on exit so that later tests' fp32 torch references stay fp32."""
 
     def __init__(self, mods):
         self.mods, self.saved = mods, {}
 
     def __enter__(self):
+        self.flags = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32, torch.is_grad_enabled())
         for k, v in self.mods.items():
             self.saved[k] = sys.modules.get(k)
             sys.modules[k] = v
         return self
 
     def __exit__(self, *exc):
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = self.flags[:2]
+        torch.set_grad_enabled(self.flags[2])
         for k, v in self.saved.items():
             if v is None:
                 sys.modules.pop(k, None)

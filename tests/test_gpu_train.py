@@ -259,7 +259,7 @@ def test_training_losses_and_parameter_gradients(name, B, T, use_l1):
         e = rel(p.grad, sdg[k].grad)
         if e > worst[1]:
             worst = (k, e)
-        assert e < 5e-2, (k, e)
+        assert e < 1e-2, (k, e)  # measured worst 4.0e-3 .. 4.6e-3 (t_embedder.mlp.0.weight)
     print(f"{name} B={B} T={T}: worst parameter-gradient rel-L2 {worst[1]:.2e} ({worst[0]})")
 
 
@@ -287,7 +287,7 @@ def test_xl_geometry_parameter_gradients():
     terms["loss"].mean().backward()
     worst = max((rel(p.grad, sdg[k].grad), k) for k, p in m.named_parameters() if p.requires_grad)
     print(f"XL geometry depth 2: worst parameter-gradient rel-L2 {worst[0]:.2e} ({worst[1]})")
-    assert worst[0] < 5e-2
+    assert worst[0] < 1e-2  # measured 4.8e-3
 
 
 def test_one_optimizer_step_reduces_the_loss():
@@ -374,7 +374,7 @@ def test_cuda_graph_training_step_matches_eager(monkeypatch):
 
 def test_loss_curve_tracks_the_oracle():
     """North star: training loss curves overlap (1 % over 1k steps).  Here: 25 AdamW steps of DiT-S on
-    identical batches / timesteps / noise, fp32 CPU oracle vs the native path, curve within 1.5 %."""
+    identical batches / timesteps / noise, fp32 CPU oracle vs the native path, every step within 1 % (measured 0.3 %)."""
     from diffusion import create_diffusion
     B, T, steps = 8, 128, 25
     shape, sd, m, (x, o, c, y, _, _) = _train_setup("DiT-S", B, T)
@@ -403,7 +403,7 @@ def test_loss_curve_tracks_the_oracle():
     dev = [abs(a - b) / abs(b) for a, b in zip(curve, ref_curve)]
     print("loss curve max rel deviation %.3e, mean %.3e; first %.4f -> last %.4f (oracle %.4f -> %.4f)"
           % (max(dev), sum(dev) / len(dev), curve[0], curve[-1], ref_curve[0], ref_curve[-1]))
-    assert max(dev) < 1.5e-2
+    assert max(dev) < 1e-2
 
 
 def test_loss_curve_1k_steps_overlaps_fp32_eager():
@@ -474,7 +474,65 @@ def test_loss_curve_1k_steps_overlaps_fp32_eager():
           f"{float(((rec['nat'] - rec['ref']).abs() / rec['ref']).max()):.2e} (twin: "
           f"{float(((rec['nat'] - rec['twin']).abs() / rec['twin']).max()):.2e})")
     assert float(rec["ref"][-1].mean()) < 0.97 * float(rec["ref"][0].mean())  # it trains
-    # within 1 %, or — where two runs of the same code differ by more — within twice that run-to-run floor
-    assert mean_dev("nat_l1", "ref_l1") < min(3e-2, max(1e-2, 3 * mean_dev("nat_l1", "twin_l1")))
-    assert med_dev("nat", "ref") < min(3e-2, max(1e-2, 3 * med_dev("nat", "twin")))
+    # the north star's 1 % (measured: L1 window means 0.17-0.22 %, total-loss window medians 0.5-0.7 % against a
+    # run-to-run floor of 0.3-0.6 % between two runs of the same code); the medians' gate widens to twice that floor
+    # only if the floor itself exceeds 0.5 %, and never beyond 2 %
+    assert mean_dev("nat_l1", "ref_l1") < 1e-2
+    assert med_dev("nat", "ref") < min(2e-2, max(1e-2, 2 * med_dev("nat", "twin")))
     assert abs(float(rec["nat_l1"].mean()) / float(rec["ref_l1"].mean()) - 1) < 1e-2  # the whole curve's mean
+
+
+def test_loss_curve_200_steps_dit_b_seq128_tracks_fp32_eager():
+    """BASELINE config 3's model and window (DiT-B, seq-len 128; batch 32 per step here): 200 AdamW steps from the
+    constructor's init on identical batches / timesteps / noise / label dropout, native path vs fp32 (TF32 off)
+    autograd over the reference's eager call sequence on the same GPU.  Compared as curves (50-step windows), see
+    test_loss_curve_1k_steps_overlaps_fp32_eager for why per-step values cannot be."""
+    import models
+    from diffusion import create_diffusion
+    from oracle import eager_cuda
+    B, T, steps, pool, win = 32, 128, 200, 4, 100
+    shape = odit.shape_of("DiT-B")
+    sd = odit.init_state_dict(shape, seed=1, zero_init_std=0.0)
+    m = models.DiT_models["DiT-B"](num_classes=52670, context_size=144, class_dropout_prob=0.2)
+    m.load_state_dict(sd, strict=True)
+    m = m.to(DEV).eval()
+    params = {k: v.clone().to(DEV).requires_grad_(v.is_floating_point() and "playfield" not in k) for k, v in sd.items()}
+    opt_ref = torch.optim.AdamW([p for p in params.values() if p.requires_grad], lr=1e-4, weight_decay=0)
+    opt = torch.optim.AdamW(m.parameters(), lr=1e-4, weight_decay=0)
+    s = odiff.Schedule("")
+    d = create_diffusion("", noise_schedule="squaredcos_cap_v2", use_l1=True)
+    batches = []
+    for i in range(pool):
+        (x, o, c), y = synth.training_batch(B, T, seed=60 + i)
+        batches.append([v.to(DEV) for v in (x, o, c, y)])
+    g = torch.Generator().manual_seed(13)
+    old = torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+    rec = {k: [] for k in ("ref", "ref_l1", "nat", "nat_l1")}
+    try:
+        for it in range(steps):
+            x, o, c, y = batches[it % pool]
+            t = torch.randint(0, 1000, (B,), generator=g).to(DEV)
+            noise = torch.randn(B, 2, T, generator=g).to(DEV)
+            yd = torch.where(torch.rand(B, generator=g).to(DEV) < 0.2, torch.full_like(y, 52670), y)
+            tr = odiff.training_losses(s, lambda xt, tt: eager_cuda.forward(params, shape.heads, xt, tt, o, c, yd),
+                                       x, t, noise, use_l1=True)
+            tr["loss"].mean().backward()
+            opt_ref.step()
+            opt_ref.zero_grad(set_to_none=True)
+            tn = d.training_losses(m, x, t, dict(o=o, c=c, y=yd), noise=noise)
+            tn["loss"].mean().backward()
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+            rec["ref"].append(tr["loss"].mean().detach()); rec["ref_l1"].append(tr["l1"].mean().detach())
+            rec["nat"].append(tn["loss"].mean().detach()); rec["nat_l1"].append(tn["l1"].mean().detach())
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+    rec = {k: torch.stack(v).cpu().double().reshape(steps // win, win) for k, v in rec.items()}
+    l1_dev = float(((rec["nat_l1"].mean(1) - rec["ref_l1"].mean(1)).abs() / rec["ref_l1"].mean(1)).max())
+    med_dev = float(((rec["nat"].median(1).values - rec["ref"].median(1).values).abs() / rec["ref"].median(1).values).max())
+    print(f"DiT-B seq 128, 200 steps: total loss {float(rec['ref'][0].mean()):.4f} -> {float(rec['ref'][-1].mean()):.4f} "
+          f"(fp32 eager) vs {float(rec['nat'][0].mean()):.4f} -> {float(rec['nat'][-1].mean()):.4f} (native); "
+          f"L1 {win}-step window means within {l1_dev:.2e}, total-loss window medians within {med_dev:.2e}")
+    assert float(rec["ref"][-1].mean()) < 0.97 * float(rec["ref"][0].mean())
+    assert l1_dev < 1e-2 and med_dev < 1.5e-2  # L1 term within the north star's 1 %; the total's median is noisier at batch 32
