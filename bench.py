@@ -410,6 +410,8 @@ def kernel_roofline(model, diffusion, zd, od, cd, yd, mask_d, device):
     ops.gemm = wrap("gemm", real_gemm, gemm_work)
     ops.ln_modulate = wrap("ln", real_ln, ln_work)
     ops.attn_band = wrap("attn", real_attn, attn_work)
+    from osudit import graphs
+    graphs_on, graphs._ENABLED = graphs._ENABLED, False  # per-launch events need the individual launches
     try:
         t = torch.full((zd.shape[0],), 50, device=device, dtype=torch.long)
         for _ in range(3):
@@ -418,6 +420,7 @@ def kernel_roofline(model, diffusion, zd, od, cd, yd, mask_d, device):
         torch.cuda.synchronize()
     finally:
         ops.gemm, ops.ln_modulate, ops.attn_band = real_gemm, real_ln, real_attn
+        graphs._ENABLED = graphs_on
 
     def agg(items, pred=lambda tag: True):
         items = [(e0.elapsed_time(e1), w) for e0, e1, (w, tag) in items if pred(tag)]

@@ -175,6 +175,12 @@ int osudit_embed_xoc(const float* x, const float* o, const float* c, const float
                      float pf_x, float pf_y, int B, int xrows, int T, int E, void* a_hi, void* a_lo,
                      void* stream);
 
+/* The x columns only (first 256 of the 384 + E): within one sampling loop o and c are the same at every denoising step
+ * (sample.py:87-108 builds them once; gaussian_diffusion.py:514-561 only updates x), so after one full osudit_embed_xoc
+ * into the same a_hi / a_lo the other 128 + E columns are left untouched. */
+int osudit_embed_x(const float* x, const float* freqs64, float pf_x, float pf_y, int B, int xrows, int T, int E,
+                   void* a_hi, void* a_lo, void* stream);
+
 /* timestep_embedding(t, 256) (positional_embedding.py:29-49) as split-bf16 [rows, 256]. */
 int osudit_timestep_features(const int64_t* t, const float* freqs128, int rows, void* hi, void* lo,
                              void* stream);

@@ -42,15 +42,18 @@ __global__ void __launch_bounds__(256)
 embed_xoc_kernel(const float* __restrict__ x, const float* __restrict__ o,
                  const float* __restrict__ c, const float* __restrict__ freqs, float pf_x, float pf_y,
                  int xrows, int T, int E, __nv_bfloat16* __restrict__ a_hi,
-                 __nv_bfloat16* __restrict__ a_lo) {
+                 __nv_bfloat16* __restrict__ a_lo, int x_only) {
   extern __shared__ float s_c[];  // [E][kTokPerCta + 1]
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * kTokPerCta;
   const int Kout = 384 + E;
   const int tid = threadIdx.x;
+  // x_only: the offset and context columns (272 of 528) do not change between the denoising steps of one sampling
+  // loop (models.py:227-233: only x is the diffusion state); they are left as a previous full call wrote them
+  const int ngrp = x_only ? 2 : 3;
 
   // context: coalesced read along T, transposed through shared memory
-  for (int idx = tid; idx < E * kTokPerCta; idx += 256) {
+  for (int idx = tid; !x_only && idx < E * kTokPerCta; idx += 256) {
     const int e = idx / kTokPerCta;
     const int tt = idx % kTokPerCta;
     const int t = t0 + tt;
@@ -61,9 +64,9 @@ embed_xoc_kernel(const float* __restrict__ x, const float* __restrict__ o,
   // sin/cos features: 3 groups (x, y, o) x 64 frequencies per token
   const float* xb = x + static_cast<int64_t>(b % xrows) * 2 * T;
   const float* ob = o + static_cast<int64_t>(b) * T;
-  for (int idx = tid; idx < kTokPerCta * 192; idx += 256) {
-    const int tt = idx / 192;
-    const int r = idx % 192;
+  for (int idx = tid; idx < kTokPerCta * ngrp * 64; idx += 256) {
+    const int tt = idx / (ngrp * 64);
+    const int r = idx % (ngrp * 64);
     const int grp = r >> 6;
     const int k = r & 63;
     const int t = t0 + tt;
@@ -80,7 +83,7 @@ embed_xoc_kernel(const float* __restrict__ x, const float* __restrict__ o,
     split_store(a_hi, a_lo, row + grp * 128 + 64 + k, sn);
   }
   __syncthreads();
-  for (int idx = tid; idx < kTokPerCta * E; idx += 256) {
+  for (int idx = tid; !x_only && idx < kTokPerCta * E; idx += 256) {
     const int tt = idx / E;
     const int e = idx % E;
     const int t = t0 + tt;
@@ -159,7 +162,19 @@ extern "C" int osudit_embed_xoc(const float* x, const float* o, const float* c, 
   dim3 grid((T + kTokPerCta - 1) / kTokPerCta, B);
   embed_xoc_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(
       x, o, c, freqs64, pf_x, pf_y, xrows, T, E, static_cast<__nv_bfloat16*>(a_hi),
-      static_cast<__nv_bfloat16*>(a_lo));
+      static_cast<__nv_bfloat16*>(a_lo), 0);
+  OSUDIT_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int osudit_embed_x(const float* x, const float* freqs64, float pf_x, float pf_y, int B, int xrows, int T,
+                              int E, void* a_hi, void* a_lo, void* stream) {
+  if (B <= 0 || T <= 0 || E < 0 || xrows <= 0) return set_error(-1, "embed_x: bad shape");
+  if (B > 65535) return set_error(-1, "embed_x: batch too large for one launch");
+  dim3 grid((T + kTokPerCta - 1) / kTokPerCta, B);
+  embed_xoc_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, nullptr, nullptr, freqs64, pf_x, pf_y, xrows, T, E, static_cast<__nv_bfloat16*>(a_hi),
+      static_cast<__nv_bfloat16*>(a_lo), 1);
   OSUDIT_CHECK_LAUNCH();
   return 0;
 }

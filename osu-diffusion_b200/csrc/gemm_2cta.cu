@@ -55,6 +55,13 @@ struct Cfg {
   static constexpr int kBiasBytes = kEpiGroups * 2 * BN * 4;  // bias slice of the current / next tile, per epilogue group
   static constexpr int kSmemBytes = kStages * kStageBytes + 2 * kEpiGroups * kStagingBytes + 1024 + kBiasBytes;
 };
+// EPI_BF16_DGELU gives one operand stage to the two TMA-staged chunks of its auxiliary operand
+__host__ __device__ constexpr int stages_for(int epi) { return epi == 4 ? kStages - 1 : kStages; }
+template <int BN>
+constexpr int smem_bytes_for(int epi) {
+  return stages_for(epi) * Cfg<BN>::kStageBytes + (epi == 4 ? 2 * kStagingBytes : 0) + 2 * kEpiGroups * kStagingBytes + 1024 +
+         Cfg<BN>::kBiasBytes;
+}
 
 struct Params {
   CUtensorMap tma_a, tma_b, tma_out, tma_aux;
@@ -173,13 +180,17 @@ template <int EPI, int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm2_kernel(const __grid_constant__ Params p) {
   constexpr int kBytesB = Cfg<BN>::kBytesB, kStageBytes = Cfg<BN>::kStageBytes;
+  constexpr int kSt = stages_for(EPI);
+  constexpr bool kAuxTma = EPI == EPI_BF16_DGELU;  // the saved GELU derivative is staged by TMA, two chunks ahead
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* staging = smem + kStages * kStageBytes;
+  uint8_t* aux_smem = smem + kSt * kStageBytes;  // [2][128 rows][64 cols] bf16, 128-byte swizzled (DGELU only)
+  uint8_t* staging = aux_smem + (kAuxTma ? 2 * kStagingBytes : 0);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + 2 * kEpiGroups * kStagingBytes);
-  uint64_t* empty_bar = full_bar + kStages;
-  uint64_t* tmem_full = empty_bar + kStages;
+  uint64_t* empty_bar = full_bar + kSt;
+  uint64_t* tmem_full = empty_bar + kSt;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* aux_full = tmem_empty + 2;  // [2] per CTA: an aux chunk has landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_full + 2);
   float* s_bias_all = reinterpret_cast<float*>(staging + 2 * kEpiGroups * kStagingBytes + 1024);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -192,14 +203,16 @@ gemm2_kernel(const __grid_constant__ Params p) {
     tma_prefetch_desc(&p.tma_a);
     tma_prefetch_desc(&p.tma_b);
     tma_prefetch_desc(&p.tma_out);
-    for (int i = 0; i < kStages; ++i) {
+    for (int i = 0; i < kSt; ++i) {
       mbar_init(&full_bar[i], 1);   // leader's: one arrive.expect_tx covering both CTAs' bytes
       mbar_init(&empty_bar[i], 1);  // per CTA: one multicast commit
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);    // per CTA: one multicast commit
       mbar_init(&tmem_empty[i], 16 * kEpiGroups);  // leader's: every epilogue warp of both CTAs
+      mbar_init(&aux_full[i], 1);
     }
+    if (kAuxTma) tma_prefetch_desc(&p.tma_aux);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -226,7 +239,7 @@ gemm2_kernel(const __grid_constant__ Params p) {
           if (leader) mbar_expect_tx(&full_bar[stage], 2 * kStageBytes);
           tma_load_2d_pair(sa, &p.tma_a, lbar, kb * BK, m0);
           tma_load_2d_pair(sa + kBytesA, &p.tma_b, lbar, kb * BK, n0);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++stage == kSt) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -257,7 +270,7 @@ gemm2_kernel(const __grid_constant__ Params p) {
           for (int k = 0; k < BK / 16; ++k)
             umma_bf16_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           umma_commit_pair(&empty_bar[stage]);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++stage == kSt) { stage = 0; phase ^= 1; }
         }
         umma_commit_pair(&tmem_full[acc]);
         GEMM_TRACE(0, it, 2);
@@ -278,21 +291,24 @@ gemm2_kernel(const __grid_constant__ Params p) {
     uint32_t acc_phase = 0;
     uint32_t chunk_ctr = 0;
     int it = 0;
+    auto aux_issue = [&](uint32_t g) {  // TMA load of running chunk g of this CTA (nothing past the last tile)
+      const int tile2 = cluster_id + static_cast<int>(g / kChunks) * n_clusters;
+      if (tile2 >= total_tiles) return;
+      const int m2 = (tile2 / p.n_tiles) * (2 * BM) + static_cast<int>(rank) * BM;
+      const int n2 = (tile2 % p.n_tiles) * BN + static_cast<int>(g % kChunks) * 64;
+      mbar_expect_tx(&aux_full[g & 1], kStagingBytes);
+      tma_load_2d(aux_smem + (g & 1) * kStagingBytes, &p.tma_aux, &aux_full[g & 1], n2, m2);
+    };
+    if (kAuxTma && ep_tid == 0) {
+      aux_issue(0);
+      aux_issue(1);
+    }
     for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++it) {
       const int m0 = (tile / p.n_tiles) * (2 * BM) + static_cast<int>(rank) * BM;
       const int n0 = (tile % p.n_tiles) * BN;
-      // EPI_BF16_DGELU: this thread's 32 pre-activations (64 B of its row) per chunk come straight from global
-      // memory; they are fetched one chunk ahead (the first one before the wait for the accumulator) so that
-      // their latency hides behind the TMEM read and the arithmetic of the current chunk.
-      uint4 ax_next[4];
-      auto load_aux = [&](int c, uint4(&dst)[4]) {
-        const bool in = m0 + row < p.M;
-        const uint4* ap = reinterpret_cast<const uint4*>(p.aux + static_cast<int64_t>(in ? m0 + row : 0) * p.ld_aux +
-                                                         n0 + c * 64 + half * 32);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) dst[j] = in ? __ldg(ap + j) : make_uint4(0u, 0u, 0u, 0u);
-      };
-      if (EPI == EPI_BF16_DGELU) load_aux(grp, ax_next);
+      // EPI_BF16_DGELU: the chunk's [128 rows][64 columns] of the saved GELU derivative arrive by TMA two chunks
+      // ahead (issued below, after the barrier that ends a chunk's reads of its buffer).  Per-thread global loads of
+      // the thread's own row cost 32 cache lines per load instruction and held this GEMM at 43 % tensor-pipe activity.
       // this tile's 256 bias values go through shared memory (one global load per thread per tile, issued before
       // the wait for the accumulator) instead of 8 dependent __ldg per thread per chunk on the critical path
       float* s_bias = s_bias_all + (grp * 2 + (it & 1)) * BN;
@@ -307,10 +323,12 @@ gemm2_kernel(const __grid_constant__ Params p) {
       for (int c = grp; c < kChunks; c += kEpiGroups) {
         const int ncol0 = n0 + c * 64;
         uint4 ax[4];
-        if (EPI == EPI_BF16_DGELU) {
+        const uint32_t gchunk = static_cast<uint32_t>(it) * kChunks + c;  // running chunk index of this CTA
+        if (kAuxTma) {
+          warp_mbar_wait(&aux_full[gchunk & 1], (gchunk >> 1) & 1);
+          const uint32_t arow = smem_u32(aux_smem + (gchunk & 1) * kStagingBytes) + row * 128;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) ax[j] = ax_next[j];
-          if (c + kEpiGroups < kChunks) load_aux(c + kEpiGroups, ax_next);
+          for (int j = 0; j < 4; ++j) ax[j] = lds128(arow + (((half * 4 + j) ^ (row & 7)) << 4));
         }
         uint32_t r[32];
         if (ep_tid == 0) GEMM_TRACE(1, it, 2 + 4 * c);
@@ -355,6 +373,7 @@ gemm2_kernel(const __grid_constant__ Params p) {
           uint8_t* buf = my_staging + (chunk_ctr & 1) * kStagingBytes;
           if (ep_tid == 0) tma_store_wait_read<1>();
           named_bar_sync(1 + grp, 256);
+          if (kAuxTma && ep_tid == 0) aux_issue(gchunk + 2);  // every thread has consumed this chunk's aux buffer
           if (ep_tid == 0) GEMM_TRACE(1, it, 2 + 4 * c + 1);
           uint8_t* my_row = buf + row * 128;
 #ifndef OSUDIT_GELU_H2
@@ -412,7 +431,7 @@ gemm2_kernel(const __grid_constant__ Params p) {
 
 template <int EPI, int BN>
 static int launch2(const Params& p, cudaStream_t stream) {
-  constexpr int kSmemBytes = Cfg<BN>::kSmemBytes;
+  constexpr int kSmemBytes = smem_bytes_for<BN>(EPI);
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(gemm2_kernel<EPI, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
@@ -468,10 +487,8 @@ int gemm_2cta_launch(const void* a, int64_t lda, const void* b, int64_t ldb, int
   p.tma_aux = p.tma_out;
   if (epilogue == EPI_BF16_GELU_SAVE || epilogue == EPI_BF16_DGELU) {
     if (aux == nullptr || (ld_aux % 8) != 0) return set_error(-1, "gemm: aux must be given with ld_aux % 8 == 0");
-    if (epilogue == EPI_BF16_GELU_SAVE) {
-      rc = make_tensor_map_2d(&p.tma_aux, aux, N, M, ld_aux * 2, 64, BM, false);
-      if (rc) return rc;
-    }
+    rc = make_tensor_map_2d(&p.tma_aux, aux, N, M, ld_aux * 2, 64, BM, false);  // SAVE: stores; DGELU: loads
+    if (rc) return rc;
   }
   switch (epilogue) {
     case EPI_BF16: return BN == 256 ? launch2<EPI_BF16, 256>(p, stream) : launch2<EPI_BF16, 192>(p, stream);

@@ -166,15 +166,16 @@ class GaussianDiffusion:
         tb = self._tables(x.device)
         t_orig = tb["tmap"][t]
         kw = dict(model_kwargs or {})
+        mod = kw.pop("_osudit_mod", None)  # adaLN modulation precomputed for this step by the sampling loop
         native = _native_dit(model)
         if native is not None:
             module, uses_cfg = native
             if uses_cfg:
                 scale = kw.pop("cfg_scale")
                 raw = module._raw_forward(x, t_orig, kw["o"], kw["c"], kw["y"], kw.get("attn_mask"),
-                                          x_rows=len(x) // 2)
+                                          x_rows=len(x) // 2, mod=mod)
                 return raw, len(x) // 2, scale
-            raw = module._raw_forward(x, t_orig, kw["o"], kw["c"], kw["y"], kw.get("attn_mask"))
+            raw = module._raw_forward(x, t_orig, kw["o"], kw["c"], kw["y"], kw.get("attn_mask"), mod=mod)
             return raw, 0, 0.0
         out = model(x, t_orig, **kw)
         if isinstance(out, tuple):
@@ -256,9 +257,23 @@ class GaussianDiffusion:
         # all step-index vectors in one upload instead of one H2D copy per step (reference :549)
         t_all = th.arange(self.num_timesteps, device=device, dtype=th.long)[:, None].expand(
             -1, shape[0]).contiguous()
+        # The conditioning path (timestep MLP + label embedding + every adaLN Linear, models.py:318-320,152-159,193)
+        # depends on (t, y) only and every t of the loop is known here: for the native DiT at GPU-bound batch sizes
+        # it is computed for all steps up front in one batched pass (launch-bound sizes replay a captured step instead)
+        mods = None
+        native = _native_dit(model)
+        if native is not None and model_kwargs is not None and "y" in model_kwargs and th.is_tensor(img) and \
+                img.is_cuda and not graphs.eligible(img) and getattr(native[0], "precision", "bf16") == "bf16" \
+                and not native[0].training:
+            module = native[0]
+            y = model_kwargs["y"].long().contiguous()
+            if y.shape == (shape[0],):
+                with th.no_grad():
+                    mods = module.engine().conditioning_steps(self._tables(device)["tmap"][t_all], y)
         for i in indices:
+            kw = model_kwargs if mods is None else dict(model_kwargs, _osudit_mod=mods[i])
             out = self.p_sample(model, img, t_all[i], clip_denoised=clip_denoised,
-                                denoised_fn=denoised_fn, cond_fn=cond_fn, model_kwargs=model_kwargs)
+                                denoised_fn=denoised_fn, cond_fn=cond_fn, model_kwargs=kw)
             yield out
             img = out["sample"]
 

@@ -166,7 +166,7 @@ class DiT(nn.Module):
             y = self.y_embedder.token_drop(y)
         return y
 
-    def _raw_forward(self, x, t, o, c, y, attn_mask, x_rows=None):
+    def _raw_forward(self, x, t, o, c, y, attn_mask, x_rows=None, mod=None):
         for name, v in (("x", x), ("t", t), ("o", o), ("c", c), ("y", y)):
             if not v.is_cuda:
                 raise RuntimeError(f"DiT.forward: `{name}` is on {v.device}; the native path runs on "
@@ -174,7 +174,7 @@ class DiT(nn.Module):
         check_inputs(self, x, t, o, c, y, x_rows)
         return self.engine().forward(x.float().contiguous(), t.long().contiguous(),
                                      o.float().contiguous(), c.float().contiguous(),
-                                     self._labels(y.long()).contiguous(), attn_mask, x_rows)
+                                     self._labels(y.long()).contiguous(), attn_mask, x_rows, mod)
 
     def _needs_grad(self):
         return torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())

@@ -40,6 +40,7 @@ SIGNATURES = {
     "osudit_ln_modulate": [_P, _P, _P, _P, _P, _L, _L, _I, _I, _P, _P, _P],
     "osudit_final_layer": [_P, _P, _P, _P, _P, _L, _L, _I, _I, _P, _P, _I, _P, _P],
     "osudit_embed_xoc": [_P, _P, _P, _P, _F, _F, _I, _I, _I, _I, _P, _P, _P],
+    "osudit_embed_x": [_P, _P, _F, _F, _I, _I, _I, _I, _P, _P, _P],
     "osudit_timestep_features": [_P, _P, _I, _P, _P, _P],
     "osudit_silu_split": [_P, _P, _P, _P, _L, _I, _P, _P, _P],
     "osudit_split_bf16": [_P, _L, _P, _P, _P],

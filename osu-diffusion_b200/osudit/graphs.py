@@ -19,7 +19,7 @@ import torch
 from . import ops
 
 _ENABLED = os.environ.get("OSUDIT_CUDA_GRAPHS", "1") != "0"
-_MAX_ROWS_TOKENS = 1 << 17  # above this a step is GPU-bound; replay would only pin extra memory
+_MAX_ROWS_TOKENS = int(os.environ.get("OSUDIT_GRAPH_MAX_ROW_TOKENS", 1 << 17))  # above: GPU-bound, replay only pins memory
 _cache: dict = {}
 
 
@@ -64,8 +64,13 @@ class StepGraph:
         B = self.x.shape[0]
         noise = torch.randn_like(self.x)  # the reference's draw (gaussian_diffusion.py:454)
         half = B // 2 if self.uses_cfg else 0
-        raw = self.module._raw_forward(self.x, self.t_orig, self.o, self.c, self.y, self.mask,
-                                       x_rows=half if self.uses_cfg else None)
+        eng = self.module.engine()
+        keep, eng.reuse_oc_columns = eng.reuse_oc_columns, False  # a replay must rewrite the whole first-layer operand
+        try:
+            raw = self.module._raw_forward(self.x, self.t_orig, self.o, self.c, self.y, self.mask,
+                                           x_rows=half if self.uses_cfg else None)
+        finally:
+            eng.reuse_oc_columns = keep
         ops.diffusion_step(raw, self.x, noise, self.t, self.tb["step"], half, self.scale, self.clip, 0,
                            self.sample, self.x0)
 
@@ -73,6 +78,8 @@ class StepGraph:
         self.x.copy_(x)
         self.t.copy_(t)
         torch.index_select(self.tb["tmap"], 0, self.t, out=self.t_orig)
+        if self.keep[0] is not None:
+            self.keep[0]["oc_sig"] = None  # the replay rewrites the shared workspace's o / c columns with ITS o / c
         self.graph.replay()
         return self.sample.clone(), self.x0.clone()
 

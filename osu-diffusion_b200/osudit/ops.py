@@ -134,6 +134,14 @@ def embed_xoc(x, o, c, freqs64, pf_x, pf_y, xrows, a_hi, a_lo):
                                     _chk(a_lo, torch.bfloat16, "embed.lo"), _stream()), "osudit_embed_xoc")
 
 
+def embed_x(x, freqs64, pf_x, pf_y, B, T, E, xrows, a_hi, a_lo):
+    """Rewrite only the 256 x columns of a_hi / a_lo [B*T, 384 + E] (the o / c columns keep a previous embed_xoc)."""
+    lib = _lib.load()
+    _lib.check(lib.osudit_embed_x(_chk(x, torch.float32, "embed.x"), _chk(freqs64, torch.float32, "embed.freqs"),
+                                  pf_x, pf_y, B, xrows, T, E, _chk(a_hi, torch.bfloat16, "embed.hi"),
+                                  _chk(a_lo, torch.bfloat16, "embed.lo"), _stream()), "osudit_embed_x")
+
+
 def timestep_features(t, freqs128, hi, lo):
     lib = _lib.load()
     _lib.check(lib.osudit_timestep_features(_chk(t, torch.int64, "tfeat.t"),

@@ -221,6 +221,65 @@ def test_shape_and_label_validation_matches_the_reference_error_behaviour():
         d.training_losses(m, z, torch.zeros(2, dtype=torch.long, device=DEV), dict(o=o, c=c[:, :100], y=y))
 
 
+# ------------------------------------------------------------------------------ step-invariant work hoisted
+@torch.no_grad()
+def test_sampling_loop_hoists_step_invariant_work_bit_exactly(monkeypatch):
+    """Within one sampling loop only x changes: the loop computes the conditioning of all steps up front in one batched
+    pass and rewrites only the x columns of the first-layer operand after the first step.  Both must
+    be invisible: the loop equals step-by-step p_sample calls (no precomputed conditioning) bit for bit, also when two
+    loops with different o / c / y alternate on the same workspace."""
+    import diffusion.gaussian_diffusion as gd
+    from diffusion import create_diffusion
+    from osudit import graphs
+    monkeypatch.setattr(graphs, "_ENABLED", False)  # the GPU-bound path (what BASELINE config 2 runs), at a test size
+    m = _model(dropout=0.1).eval()
+    d = create_diffusion("8", noise_schedule="squaredcos_cap_v2")
+    T = 200
+    mask = synth.band_mask(T, 128).to(DEV)
+    sets = []
+    for seed in (1, 2):
+        z, o, c, y = [v.to(DEV) for v in synth.sampling_batch(2, T, seed=seed)]
+        sets.append((z, dict(o=o, c=c, y=y, cfg_scale=1.5, attn_mask=mask)))
+    g = torch.Generator().manual_seed(0)
+    noises = [torch.randn(4, 2, T, generator=g).to(DEV) for _ in range(8)]
+
+    def with_noise(fn):
+        it = iter(noises)
+        real = gd.th.randn_like
+        gd.th.randn_like = lambda v: next(it)
+        try:
+            return fn()
+        finally:
+            gd.th.randn_like = real
+
+    def stepwise(z, kw):  # plain p_sample calls: conditioning computed inside every forward, fresh engine each time
+        m._engine = None
+        x = z
+        for i in reversed(range(8)):
+            m.engine().reuse_oc_columns = False
+            x = d.p_sample(m.forward_with_cfg, x, torch.full((4,), i, device=DEV), model_kwargs=kw)["sample"]
+        m._engine = None
+        return x
+
+    want = [with_noise(lambda: stepwise(z, kw)) for z, kw in sets]
+    calls = {"x": 0, "xoc": 0}
+    from osudit import ops
+    real_x, real_xoc = ops.embed_x, ops.embed_xoc
+    monkeypatch.setattr(ops, "embed_x", lambda *a, **k: (calls.__setitem__("x", calls["x"] + 1), real_x(*a, **k))[1])
+    monkeypatch.setattr(ops, "embed_xoc", lambda *a, **k: (calls.__setitem__("xoc", calls["xoc"] + 1), real_xoc(*a, **k))[1])
+    got = [with_noise(lambda: d.p_sample_loop(m.forward_with_cfg, z.shape, z, model_kwargs=kw, device=DEV))
+           for z, kw in sets]
+    assert calls == {"x": 14, "xoc": 2}  # one full operand per loop, then x columns only
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
+    # alternating the two conditioning sets step by step on the same workspace: every switch rewrites everything
+    calls.update(x=0, xoc=0)
+    for i in (7, 6):
+        for z, kw in sets:
+            d.p_sample(m.forward_with_cfg, z, torch.full((4,), i, device=DEV), model_kwargs=kw)
+    assert calls == {"x": 0, "xoc": 4}
+
+
 # ------------------------------------------------------------------------------ data-parallel gradients
 def _ddp_worker(rank, world, port, backend, q, use_wrap):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
