@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
         const int h = prob % p.H, b = prob / p.H;
         const int st = i & 1;
         uint8_t* base = smem + st * kStage;
-        mbar_wait(&in_free[st], ((i >> 1) & 1) ^ 1);
+        mbar_wait_sleep(&in_free[st], ((i >> 1) & 1) ^ 1, 200);
         mbar_expect_tx(&in_full[st], kStage);
         tma_load_3d(base + 0 * kTile, &p.tma_qkv, &in_full[st], h * kHD, 0, b);
         tma_load_3d(base + 1 * kTile, &p.tma_qkv, &in_full[st], p.D + h * kHD, 0, b);
@@ -187,11 +187,11 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
       if (n_my > 0) issue_sdp(0);
       for (int i = 0; i < n_my; ++i) {
         BWD_TRACE(0, i, 0);
-        mbar_wait(p_full, i & 1);  // S / dP of problem i read, P / dS in shared memory
+        mbar_wait_sleep(p_full, i & 1, 32);  // S / dP of problem i read, P / dS in shared memory
         BWD_TRACE(0, i, 1);
         if (i + 1 < n_my) issue_sdp(i + 1);
         BWD_TRACE(0, i, 2);
-        mbar_wait(g_free, (i & 1) ^ 1);  // the epilogue has read problem i-1's gradients out of TMEM
+        mbar_wait_sleep(g_free, (i & 1) ^ 1, 32);  // the epilogue has read problem i-1's gradients out of TMEM
         BWD_TRACE(0, i, 3);
         tc_fence_after();
         const uint32_t base = smem_u32(smem + (i & 1) * kStage);
@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
       }
       named_bar_sync(1, 256);
       const float delta = s_delta[row] + s_delta[kT + row];
-      warp_mbar_wait(sdp_full, i & 1);
+      warp_mbar_wait_sleep(sdp_full, i & 1, 20);
       if (tracer) BWD_TRACE(1, i, 1);
       tc_fence_after();
 #pragma unroll 1
@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
       const int h = prob % p.H, b = prob / p.H;
       const bool tracer = warp == 12 && lane == 0;
       if (tracer) BWD_TRACE(2, i, 0);
-      warp_mbar_wait(g_full, i & 1);
+      warp_mbar_wait_sleep(g_full, i & 1, 40);
       if (tracer) BWD_TRACE(2, i, 1);
       tc_fence_after();
       uint8_t* stage = smem + (i & 1) * kStage;

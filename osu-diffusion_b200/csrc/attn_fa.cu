@@ -193,17 +193,17 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fa_kernel(const __grid_const
       uint32_t kn = 0, vn = 0, tn = 0;
       for (int tile = 2 * static_cast<int>(blockIdx.x) + s; tile < p.total_tiles; tile += 2 * G, ++tn) {
         const Tile t = decode_tile(p, tile);
-        mbar_wait(bar.q_free, (tn & 1) ^ 1);  // every S MMA of this slot's previous tile has read Q
+        mbar_wait_sleep(bar.q_free, (tn & 1) ^ 1, 200);  // every S MMA of this slot's previous tile has read Q
         mbar_expect_tx(bar.q_full, kTile);
         tma_load_3d(base + kOffQ, &p.tma_qkv, bar.q_full, t.h * kHD, t.q0, t.b);
         for (int j = 0; j < t.n_slabs; ++j) {
           const int k0 = (t.slab_lo + j) * kS;
           const uint32_t ks = kn & 1, vs = vn & 1;
-          mbar_wait(&bar.k_free[ks], ((kn >> 1) & 1) ^ 1);
+          mbar_wait_sleep(&bar.k_free[ks], ((kn >> 1) & 1) ^ 1, 200);
           mbar_expect_tx(&bar.k_full[ks], kTile);
           tma_load_3d(base + kOffK + ks * kTile, &p.tma_qkv, &bar.k_full[ks], p.D + t.h * kHD, k0, t.b);
           ++kn;
-          mbar_wait(&bar.v_free[vs], ((vn >> 1) & 1) ^ 1);
+          mbar_wait_sleep(&bar.v_free[vs], ((vn >> 1) & 1) ^ 1, 200);
           mbar_expect_tx(&bar.v_full[vs], kTile);
           tma_load_3d(base + kOffV + vs * kTile, &p.tma_qkv, &bar.v_full[vs], 2 * p.D + t.h * kHD, k0, t.b);
           ++vn;
@@ -253,11 +253,11 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fa_kernel(const __grid_const
       };
       for (int tile = 2 * static_cast<int>(blockIdx.x) + s; tile < p.total_tiles; tile += 2 * G, ++tn) {
         const int n = decode_tile(p, tile).n_slabs;
-        mbar_wait(bar.q_full, tn & 1);
+        mbar_wait_sleep(bar.q_full, tn & 1, 64);
         issue_s();
         for (int j = 0; j < n; ++j, ++sn) {
           FA_TRACE(s, 0, sn, 0);
-          mbar_wait(bar.p_full, sn & 1);  // S(j) read, P(j) in shared memory
+          mbar_wait_sleep(bar.p_full, sn & 1, 32);  // S(j) read, P(j) in shared memory
           FA_TRACE(s, 0, sn, 1);
           if (j + 1 < n) issue_s();
           FA_TRACE(s, 0, sn, 2);
@@ -412,7 +412,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fa_kernel(const __grid_const
 
         const bool tracer = quad == 0 && lane == 0;
         if (tracer) FA_TRACE(s, 1, sn, 0);
-        warp_mbar_wait(bar.s_full, sn & 1);
+        warp_mbar_wait_sleep(bar.s_full, sn & 1, 20);
         if (tracer) FA_TRACE(s, 1, sn, 1);
         tc_fence_after();
         uint32_t ra[32], rb[32];

@@ -63,12 +63,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// For waits that are expected to take long (a producer waiting for a buffer to drain): try_wait returns after a few
+// tens of cycles when the phase is still open, so a bare loop issues a probe + branch every ~20 cycles for the whole
+// wait (ncu counted 10 M probes per launch in the attention kernel) and competes with the working warps of the same
+// scheduler for issue slots and for the shared-memory pipe.  Sleeping between probes costs at most `ns` of latency.
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
+}
+
 // Warp-collective forms: one lane polls / arrives for the whole (converged) warp.  With hundreds of
 // threads spinning on try_wait the mbarrier unit saturates and every arrive / complete_tx / commit
 // queues behind the polls, so hand-off latency grows from ~175 cycles to thousands (measured with
 // tools/ubench and the attention kernel's ablations); barrier counts are per WARP accordingly.
 __device__ __forceinline__ void warp_mbar_wait(uint64_t* bar, uint32_t parity) {
   if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
+  __syncwarp();
+}
+__device__ __forceinline__ void warp_mbar_wait_sleep(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  if ((threadIdx.x & 31) == 0) mbar_wait_sleep(bar, parity, ns);
   __syncwarp();
 }
 __device__ __forceinline__ void warp_mbar_arrive(uint64_t* bar) {
