@@ -93,6 +93,16 @@ int osudit_attn_band_bwd(const void* qkv, const void* out, const void* dout, con
 int osudit_transpose_bf16(const void* in, void* out, int64_t rows, int64_t cols, int64_t out_ld, int in_is_f32,
                           void* stream);
 
+/* Every GEMM-ready copy of every fp32 weight matrix in one launch: what the reference gets from autocast's per-call
+ * casts (train.py:249-255) and what the native backward needs transposed.  `segments` is a DEVICE array of `nseg`
+ * records, sorted by tile0:
+ *   struct { const float* src; void* copy; void* trans; void* hi; void* lo; int64_t ld_trans;
+ *            int32_t rows, cols, tile0, tiles_x; }            (64 bytes)
+ * src fp32 [rows, cols]; copy bf16 [rows, cols]; trans bf16 [cols, ld_trans] with trans[c][r] = src[r][c]; hi / lo
+ * split-bf16 [rows, cols]; any destination may be NULL.  A segment owns tiles [tile0, tile0 + tiles_x * ceil(rows/64))
+ * of 64 x 64 elements, tiles_x = ceil(cols/64); total_tiles is the launch grid. */
+int osudit_repack_weights(const void* segments, int nseg, int total_tiles, void* stream);
+
 /* nn.GELU(approximate="tanh") of the Mlp and its derivative (models.py:112-119):
  * backward == 0: out = gelu_tanh(pre);  backward == 1: out = dy * gelu_tanh'(pre).  bf16, n % 8 == 0. */
 int osudit_gelu(const void* pre, const void* dy, void* out, int64_t n, int backward, void* stream);

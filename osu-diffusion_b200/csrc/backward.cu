@@ -77,6 +77,60 @@ transpose_f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __rest
   }
 }
 
+// ------------------------------------------------------------------ batched weight re-pack
+// Every GEMM-ready copy of every fp32 nn.Linear weight in ONE launch (the training step re-packs all of them after each
+// optimizer update, train.py:258-261): same-layout bf16 (forward operand), transposed bf16 (data-gradient operand),
+// split-bf16 hi / lo (the precision-critical small GEMMs).  One CTA per 64 x 64 tile of some matrix; the per-matrix
+// launches it replaces (50 transposes + 48 casts + 21 splits of 10 us each) were launch-latency bound at ~1 TB/s.
+struct RepackSeg {       // mirrored by osudit/train.py (numpy structured dtype) and include/osudit.h
+  const float* src;      // fp32 [rows, cols] row-major
+  __nv_bfloat16* copy;   // bf16 [rows, cols] or null
+  __nv_bfloat16* trans;  // bf16 [cols, ld_trans] (element (c, r) = src[r][c]) or null
+  __nv_bfloat16* hi;     // split-bf16 [rows, cols] or null
+  __nv_bfloat16* lo;
+  int64_t ld_trans;
+  int32_t rows, cols;
+  int32_t tile0, tiles_x;  // first tile index of this segment in the launch, tiles per row of tiles
+};
+
+__global__ void __launch_bounds__(256) repack_weights_kernel(const RepackSeg* __restrict__ segs, int nseg) {
+  __shared__ float tile[64][65];
+  __shared__ RepackSeg sg;
+  if (threadIdx.x == 0) {
+    int lo = 0, hi = nseg - 1;  // last segment whose tile0 <= blockIdx.x
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (segs[mid].tile0 <= static_cast<int>(blockIdx.x)) lo = mid; else hi = mid - 1;
+    }
+    sg = segs[lo];
+  }
+  __syncthreads();
+  const int t = static_cast<int>(blockIdx.x) - sg.tile0;
+  const int r0 = (t / sg.tiles_x) * 64, c0 = (t % sg.tiles_x) * 64;
+  for (int i = threadIdx.x; i < 64 * 64; i += 256) {
+    const int r = i >> 6, c = i & 63;
+    const bool in = r0 + r < sg.rows && c0 + c < sg.cols;
+    const int64_t idx = static_cast<int64_t>(r0 + r) * sg.cols + c0 + c;
+    const float v = in ? sg.src[idx] : 0.f;
+    tile[r][c] = v;
+    if (in) {
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      if (sg.copy) sg.copy[idx] = h;
+      if (sg.hi) {
+        sg.hi[idx] = h;
+        sg.lo[idx] = __float2bfloat16_rn(v - __bfloat162float(h));
+      }
+    }
+  }
+  if (sg.trans == nullptr) return;
+  __syncthreads();
+  for (int i = threadIdx.x; i < 64 * 64; i += 256) {
+    const int c = i >> 6, r = i & 63;
+    if (c0 + c < sg.cols && r0 + r < sg.rows)
+      sg.trans[static_cast<int64_t>(c0 + c) * sg.ld_trans + r0 + r] = __float2bfloat16_rn(tile[r][c]);
+  }
+}
+
 // ---------------------------------------------------------------------------------- GELU
 __device__ __forceinline__ float gelu_tanh_f(float x) {
   const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
@@ -649,6 +703,14 @@ extern "C" int osudit_transpose_bf16(const void* in, void* out, int64_t rows, in
   else
     transpose_bf16_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(in),
                                                static_cast<__nv_bfloat16*>(out), rows, cols, out_ld);
+  OSUDIT_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int osudit_repack_weights(const void* segments, int nseg, int total_tiles, void* stream) {
+  if (segments == nullptr || nseg <= 0 || total_tiles <= 0) return set_error(-1, "repack_weights: bad arguments");
+  repack_weights_kernel<<<total_tiles, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const RepackSeg*>(segments), nseg);
   OSUDIT_CHECK_LAUNCH();
   return 0;
 }

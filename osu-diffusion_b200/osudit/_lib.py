@@ -27,6 +27,7 @@ SIGNATURES = {
     "osudit_gemm_wgrad": [_P, _L, _P, _L, _L, _L, _L, _P, _L, _P],
     "osudit_attn_band_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P],
     "osudit_transpose_bf16": [_P, _P, _L, _L, _L, _I, _P],
+    "osudit_repack_weights": [_P, _I, _I, _P],
     "osudit_gelu": [_P, _P, _P, _L, _I, _P],
     "osudit_colsum": [_P, _I, _L, _I, _P, _P],
     "osudit_gate_residual_bwd": [_P, _P, _P, _P, _L, _I, _I, _I, _P, _P, _P],

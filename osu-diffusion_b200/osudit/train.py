@@ -22,23 +22,89 @@ from . import ops
 from .engine import FREQ_SEQ, FREQ_T, check_label_range, classify_mask
 
 
-def _bf(p):
-    return p.detach().to(torch.bfloat16).contiguous()
+_SEG_DTYPE = None
 
 
-def _wt(p):
-    """Transposed bf16 copy of an nn.Linear weight [out, in] -> [in, out] (the B operand of dgrad)."""
-    p = p.detach()
-    if p.dtype == torch.float32 and p.is_contiguous() and p.shape[0] % 8 == 0:
-        return ops.transpose(p)  # tiled fp32 -> bf16 transpose (csrc/backward.cu)
-    return p.t().to(torch.bfloat16).contiguous()
+def _seg_dtype():
+    global _SEG_DTYPE
+    if _SEG_DTYPE is None:
+        import numpy as np
+        _SEG_DTYPE = np.dtype([("src", "<u8"), ("copy", "<u8"), ("trans", "<u8"), ("hi", "<u8"), ("lo", "<u8"),
+                               ("ld_trans", "<i8"), ("rows", "<i4"), ("cols", "<i4"), ("tile0", "<i4"), ("tiles_x", "<i4")])
+        assert _SEG_DTYPE.itemsize == 64  # struct RepackSeg, csrc/backward.cu
+    return _SEG_DTYPE
 
 
 class TrainWeights:
-    """bf16 / split-bf16 / transposed copies of the parameters, rebuilt when a version changes."""
+    """bf16 / split-bf16 / transposed copies of the parameters, rebuilt when a version changes.
+
+    The destinations are allocated once per parameter set and ALL of them are refreshed by one launch
+    (`osudit_repack_weights`, a table of 64 x 64 tiles over every weight matrix): same-layout bf16 for the forward
+    GEMMs, transposed bf16 (zero-padded to a multiple of 8 columns) for the data-gradient GEMMs, hi / lo splits for the
+    precision-critical small GEMMs; the adaLN Linears of all blocks land directly in their slices of one stacked
+    matrix (no torch.cat)."""
 
     def __init__(self):
         self.sig = None
+        self.ptr_sig = None
+
+    def _build(self, model):
+        import numpy as np
+        dev = next(model.parameters()).device
+        bf = lambda *s: torch.empty(*s, dtype=torch.bfloat16, device=dev)  # noqa: E731
+        zbf = lambda *s: torch.zeros(*s, dtype=torch.bfloat16, device=dev)  # noqa: E731
+        segs = []
+
+        def add(p, copy=None, trans=None, trans_off=0, hi=None, lo=None):
+            w = p.detach()
+            if w.dtype != torch.float32 or not w.is_contiguous() or not w.is_cuda:
+                raise RuntimeError("the native training path needs contiguous fp32 CUDA parameters")
+            rows, cols = w.shape
+            segs.append((w.data_ptr(), copy.data_ptr() if copy is not None else 0,
+                         trans.data_ptr() + 2 * trans_off if trans is not None else 0,
+                         hi.data_ptr() if hi is not None else 0, lo.data_ptr() if lo is not None else 0,
+                         trans.stride(0) if trans is not None else 0, rows, cols))
+
+        def split_of(p):
+            hi, lo = bf(*p.shape), bf(*p.shape)
+            return hi, lo
+
+        def trans_of(p):  # [out, in] -> [in, pad8(out)], the pad columns stay zero
+            return zbf(p.shape[1], ops._pad8(p.shape[0]))
+
+        first, t0, t2 = model.xoc_embedder.mlp[0].weight, model.t_embedder.mlp[0].weight, model.t_embedder.mlp[2].weight
+        self.first_w, self.t0_w, self.t2_w = split_of(first), split_of(t0), split_of(t2)
+        self.t2_wt = trans_of(t2)
+        add(first, hi=self.first_w[0], lo=self.first_w[1])
+        add(t0, hi=self.t0_w[0], lo=self.t0_w[1])
+        add(t2, hi=self.t2_w[0], lo=self.t2_w[1], trans=self.t2_wt)
+        mods = [b.adaLN_modulation[1] for b in model.blocks] + [model.final_layer.adaLN_modulation[1]]
+        total = sum(m.weight.shape[0] for m in mods)
+        D = mods[0].weight.shape[1]
+        self.mod_w = (bf(total, D), bf(total, D))
+        self.mod_wt = zbf(D, ops._pad8(total))
+        r = 0
+        for m in mods:
+            n = m.weight.shape[0]
+            add(m.weight, hi=self.mod_w[0][r:r + n], lo=self.mod_w[1][r:r + n], trans=self.mod_wt, trans_off=r)
+            r += n
+        self._mod_biases = [m.bias for m in mods]
+        self.blocks = []
+        for blk in model.blocks:
+            d = {}
+            for name, p in (("qkv", blk.attn.in_proj_weight), ("out", blk.attn.out_proj.weight),
+                            ("fc1", blk.mlp.fc1.weight), ("fc2", blk.mlp.fc2.weight)):
+                d[name + "_w"], d[name + "_wt"] = bf(*p.shape), trans_of(p)
+                add(p, copy=d[name + "_w"], trans=d[name + "_wt"])
+            self.blocks.append(d)
+        tab = np.zeros(len(segs), dtype=_seg_dtype())
+        tile0 = 0
+        for i, (src, copy, trans, hi, lo, ldt, rows, cols) in enumerate(segs):
+            tx = (cols + 63) // 64
+            tab[i] = (src, copy, trans, hi, lo, ldt, rows, cols, tile0, tx)
+            tile0 += tx * ((rows + 63) // 64)
+        self._table = torch.from_numpy(tab.view(np.uint8).copy()).to(dev)
+        self._nseg, self._tiles = len(segs), tile0
 
     def refresh(self, model):
         pfp = model.xoc_embedder.playfield_size  # frozen: read it back (a host sync) only when it changes
@@ -49,22 +115,16 @@ class TrainWeights:
         sig = tuple((p.data_ptr(), p._version) for p in model.parameters())
         if sig == self.sig:
             return self
-        self.first_w = ops.split_bf16(model.xoc_embedder.mlp[0].weight)
-        self.t0_w = ops.split_bf16(model.t_embedder.mlp[0].weight)
-        self.t2_w = ops.split_bf16(model.t_embedder.mlp[2].weight)
-        self.t2_wt = _wt(model.t_embedder.mlp[2].weight)
-        mods = [b.adaLN_modulation[1] for b in model.blocks] + [model.final_layer.adaLN_modulation[1]]
-        mod_w = torch.cat([m.weight.detach() for m in mods], 0)
-        self.mod_w = ops.split_bf16(mod_w)
-        self.mod_wt = _wt(mod_w)
-        self.mod_b = torch.cat([m.bias.detach() for m in mods], 0).float().contiguous()
-        self.blocks = []
-        for blk in model.blocks:
-            self.blocks.append(dict(
-                qkv_w=_bf(blk.attn.in_proj_weight), qkv_wt=_wt(blk.attn.in_proj_weight),
-                out_w=_bf(blk.attn.out_proj.weight), out_wt=_wt(blk.attn.out_proj.weight),
-                fc1_w=_bf(blk.mlp.fc1.weight), fc1_wt=_wt(blk.mlp.fc1.weight),
-                fc2_w=_bf(blk.mlp.fc2.weight), fc2_wt=_wt(blk.mlp.fc2.weight)))
+        ptr_sig = tuple(s[0] for s in sig)
+        if ptr_sig != self.ptr_sig:  # first use, or the parameters moved (.to(), load into new storage): new table
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("TrainWeights: the re-pack table must exist before a CUDA graph is captured")
+            self._build(model)
+            self.ptr_sig = ptr_sig
+        lib = ops._lib.load()
+        ops._lib.check(lib.osudit_repack_weights(self._table.data_ptr(), self._nseg, self._tiles, ops._stream()),
+                       "osudit_repack_weights")
+        self.mod_b = torch.cat([b.detach() for b in self._mod_biases], 0).float().contiguous()
         self.sig = sig
         return self
 
@@ -153,16 +213,43 @@ def forward_train(model, tw: TrainWeights, x, t, o, c, y, attn_mask):
     return out, S
 
 
-def _wgrad(dy, x, dev):
-    """dW[out, in] = dY[rows, out]^T . X[rows, in], read token-major (no transposes), fp32."""
-    return ops.gemm_wgrad(dy, x, torch.zeros(dy.shape[1], x.shape[1], dtype=torch.float32, device=dev))
+class _Zeros:
+    """Zero-initialised fp32 gradient buffers of one backward piece, carved out of ONE allocation (one memset instead
+    of a fill launch per parameter): the weight-gradient GEMM and the bias column sums accumulate into them.  The
+    total is learnt on the piece's first run (which still allocates per tensor)."""
+    totals: dict = {}
+
+    def __init__(self, key, dev):
+        self.key, self.dev, self.off, self.used = key, dev, 0, 0
+        n = _Zeros.totals.get(key, 0)
+        self.buf = torch.zeros(n, dtype=torch.float32, device=dev) if n else None
+
+    def __call__(self, *shape):
+        n = 1
+        for v in shape:
+            n *= int(v)
+        step = (n + 63) // 64 * 64  # 256-byte aligned slices (TMA reduce-add needs 16)
+        self.used += step
+        if self.buf is None or self.off + n > self.buf.numel():
+            return torch.zeros(*shape, dtype=torch.float32, device=self.dev)
+        out = self.buf[self.off:self.off + n].view(*shape)
+        self.off += step
+        return out
+
+    def close(self):
+        _Zeros.totals[self.key] = max(self.used, _Zeros.totals.get(self.key, 0))
 
 
-def _wgrad_small(dy_f32, x_bf16, dev):
+def _wgrad(dy, x, z):
+    """dW[out, in] = dY[rows, out]^T . X[rows, in], read token-major (no transposes), fp32, into a zeroed buffer of `z`."""
+    return ops.gemm_wgrad(dy, x, z(dy.shape[1], x.shape[1]))
+
+
+def _wgrad_small(dy_f32, x_bf16, z):
     """Same for the per-sample (conditioning) matrices whose row count is the batch size: the fp32
     gradient is rounded to bf16 first."""
     dy_bf, _ = ops.split_bf16(dy_f32, need_lo=False)
-    return _wgrad(dy_bf, x_bf16, dev)
+    return _wgrad(dy_bf, x_bf16, z)
 
 
 # ------------------------------------------------------------------------------ backward, in pieces
@@ -175,12 +262,12 @@ class _Bwd:
     __slots__ = ("dx", "dmod", "dy_buf", "dh_buf", "dy2")
 
 
-def _adaln_grads(S, dmod_cols, lin, dev):
+def _adaln_grads(S, dmod_cols, lin, z):
     """Gradients of one adaLN Linear (mod = SiLU(cond) W^T + b) from its finished columns of dmod."""
     dm = dmod_cols.contiguous()
     dm_bf, _ = ops.split_bf16(dm, need_lo=False)
-    gw = _wgrad(dm_bf, S["c_hi"], dev)
-    gb = ops.colsum(dm, torch.zeros(dm.shape[1], dtype=torch.float32, device=dev))
+    gw = _wgrad(dm_bf, S["c_hi"], z)
+    gb = ops.colsum(dm, z(dm.shape[1]))
     return {lin.weight: gw, lin.bias: gb}
 
 
@@ -189,7 +276,7 @@ def bwd_final(model, tw: TrainWeights, S, dout):
     B, T = S["B"], S["T"]
     D, depth = model.hidden_size, len(model.blocks)
     rows, dev, mod = B * T, dout.device, S["mod"]
-    z32 = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)  # noqa: E731
+    z32 = _Zeros(("final", D, depth, B), dev)
     bs, grads = _Bwd(), {}
     bs.dmod = z32(B, mod.shape[1])
     bs.dx = _e(rows, D, dtype=torch.float32, device=dev)
@@ -199,7 +286,7 @@ def bwd_final(model, tw: TrainWeights, S, dout):
     ops.final_layer_bwd(S["xf"], dout.contiguous(), mod, bs.dmod, fbase, fbase + D, B, T,
                         fl.linear.weight.detach().float().contiguous(), grads[fl.linear.weight],
                         grads[fl.linear.bias], bs.dx)
-    grads.update(_adaln_grads(S, bs.dmod[:, fbase:fbase + 2 * D], fl.adaLN_modulation[1], dev))
+    grads.update(_adaln_grads(S, bs.dmod[:, fbase:fbase + 2 * D], fl.adaLN_modulation[1], z32))
     # Bias gradients are the column sums of the branch gradients and are accumulated by the kernels that
     # produce those.  Along the residual stream each LayerNorm backward is fused with the gated-residual
     # backward that follows it (ops.ln_gate_bwd); only the very first gate (last block's MLP) stands alone.
@@ -208,6 +295,7 @@ def bwd_final(model, tw: TrainWeights, S, dout):
     grads[last.mlp.fc2.bias] = z32(D)  # handed out by the last block's piece
     bs.dy2 = ops.gate_residual_bwd(bs.dx, S["blocks"][depth - 1]["y2"], mod, bs.dmod, 6 * D * (depth - 1) + 5 * D,
                                    B, T, bs.dy_buf, dbias=grads[last.mlp.fc2.bias])
+    z32.close()
     return bs, grads
 
 
@@ -217,29 +305,29 @@ def bwd_block(model, tw: TrainWeights, S, bs, i, carry):
     B, T, spec = S["B"], S["T"], S["spec"]
     D, H = model.hidden_size, model.num_heads
     rows, dev, mod, dmod, dx = B * T, bs.dx.device, S["mod"], bs.dmod, bs.dx
-    z32 = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)  # noqa: E731
+    z32 = _Zeros(("block", D, model.blocks[0].mlp.fc1.weight.shape[0], i > 0), dev)
     blk, bw, sv = model.blocks[i], tw.blocks[i], S["blocks"][i]
     base = 6 * D * i
     hidden = sv["pre"].shape[1]
     grads = {blk.mlp.fc2.bias: carry}
     dy2 = bs.dy2
     # ---- MLP branch: x_out = xb + gate_mlp * y2 (dy2 = gate_mlp * dx is already in dy_buf)
-    grads[blk.mlp.fc2.weight] = _wgrad(dy2, sv["u"], dev)
+    grads[blk.mlp.fc2.weight] = _wgrad(dy2, sv["u"], z32)
     # d pre = (dy2 W2) * gelu'(pre): the saved derivative is applied in the data-gradient GEMM's epilogue
     dpre = ops.gemm_aux(dy2, bw["fc2_wt"], None, ops.EPI_BF16_DGELU, _e(rows, hidden, device=dev), sv["pre"])
     grads[blk.mlp.fc1.bias] = ops.colsum(dpre, z32(hidden))
-    grads[blk.mlp.fc1.weight] = _wgrad(dpre, sv["h2"], dev)
+    grads[blk.mlp.fc1.weight] = _wgrad(dpre, sv["h2"], z32)
     dh2 = ops.gemm([dpre], [bw["fc1_wt"]], None, ops.EPI_BF16, bs.dh_buf)
     # ---- LN2 backward into dx, then the attention branch's gate: xb = xa + gate_msa * y1
     grads[blk.attn.out_proj.bias] = z32(D)
     dy1 = ops.ln_gate_bwd(sv["xb"], dh2, mod, dmod, base + 3 * D, base + 4 * D, B, T, dx, True,
                           y=sv["y1"], gate_col=base + 2 * D, dy=bs.dy_buf, dbias=grads[blk.attn.out_proj.bias])
-    grads[blk.attn.out_proj.weight] = _wgrad(dy1, sv["att"], dev)
+    grads[blk.attn.out_proj.weight] = _wgrad(dy1, sv["att"], z32)
     datt = ops.gemm([dy1], [bw["out_wt"]], None, ops.EPI_BF16, bs.dh_buf)
     grads[blk.attn.in_proj_bias] = z32(3 * D)
     dqkv = ops.attn_band_bwd(sv["qkv"], sv["att"], datt, sv["lse"], _e(rows, 3 * D, device=dev), B, T, H,
                              D // H, spec.w_left, spec.w_right, dbias=grads[blk.attn.in_proj_bias])
-    grads[blk.attn.in_proj_weight] = _wgrad(dqkv, sv["h1"], dev)
+    grads[blk.attn.in_proj_weight] = _wgrad(dqkv, sv["h1"], z32)
     dh1 = ops.gemm([dqkv], [bw["qkv_wt"]], None, ops.EPI_BF16, bs.dh_buf)
     # ---- LN1 backward into dx, then the previous block's MLP gate
     new_carry = None
@@ -250,7 +338,8 @@ def bwd_block(model, tw: TrainWeights, S, bs, i, carry):
     else:
         ops.ln_gate_bwd(sv["xa"], dh1, mod, dmod, base, base + D, B, T, dx, True)
     # every column of this block's slice of dmod is final now (its MLP gate was accumulated one piece earlier)
-    grads.update(_adaln_grads(S, dmod[:, base:base + 6 * D], blk.adaLN_modulation[1], dev))
+    grads.update(_adaln_grads(S, dmod[:, base:base + 6 * D], blk.adaLN_modulation[1], z32))
+    z32.close()
     return grads, new_carry
 
 
@@ -260,10 +349,10 @@ def bwd_head(model, tw: TrainWeights, S, bs):
     B = S["B"]
     D = model.hidden_size
     dev, dx, dmod = bs.dx.device, bs.dx, bs.dmod
-    z32 = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)  # noqa: E731
+    z32 = _Zeros(("head", D, model.y_embedder.embedding_table.weight.shape[0], model.context_size), dev)
     grads = {}
     first = model.xoc_embedder.mlp[0]
-    grads[first.weight] = _wgrad_small(dx, S["a_hi"], dev)
+    grads[first.weight] = _wgrad_small(dx, S["a_hi"], z32)
     grads[first.bias] = ops.colsum(dx, z32(D))
     dmod_bf, _ = ops.split_bf16(dmod, need_lo=False)
     ds = ops.gemm([dmod_bf], [tw.mod_wt], None, ops.EPI_F32, _e(B, D, dtype=torch.float32, device=dev))
@@ -272,12 +361,13 @@ def bwd_head(model, tw: TrainWeights, S, bs):
     dcond = ops.silu_bwd(S["temb"], ds, torch.empty_like(ds), table=S["table"], y=S["y"], dtable=grads[table_p])
     t0, t2 = model.t_embedder.mlp[0], model.t_embedder.mlp[2]
     dcond_bf, _ = ops.split_bf16(dcond, need_lo=False)
-    grads[t2.weight] = _wgrad(dcond_bf, S["s1_hi"], dev)
+    grads[t2.weight] = _wgrad(dcond_bf, S["s1_hi"], z32)
     grads[t2.bias] = ops.colsum(dcond, z32(D))
     ds1 = ops.gemm([dcond_bf], [tw.t2_wt], None, ops.EPI_F32, torch.empty_like(ds))
     dh1t = ops.silu_bwd(S["h1t"], ds1, torch.empty_like(ds1))
-    grads[t0.weight] = _wgrad_small(dh1t, S["tf_hi"], dev)
+    grads[t0.weight] = _wgrad_small(dh1t, S["tf_hi"], z32)
     grads[t0.bias] = ops.colsum(dh1t, z32(D))
+    z32.close()
     return grads
 
 
