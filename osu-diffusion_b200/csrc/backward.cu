@@ -107,6 +107,35 @@ __global__ void __launch_bounds__(256) repack_weights_kernel(const RepackSeg* __
   __syncthreads();
   const int t = static_cast<int>(blockIdx.x) - sg.tile0;
   const int r0 = (t / sg.tiles_x) * 64, c0 = (t % sg.tiles_x) * 64;
+  const bool vec = (sg.cols & 3) == 0 && (sg.rows & 3) == 0 && (sg.ld_trans & 3) == 0;  // every nn.Linear of the model
+  if (vec) {
+    for (int i = threadIdx.x; i < 64 * 16; i += 256) {  // 16-byte loads, 8-byte bf16 stores
+      const int r = i >> 4, c = (i & 15) * 4;
+      const bool in = r0 + r < sg.rows && c0 + c < sg.cols;
+      const int64_t idx = static_cast<int64_t>(r0 + r) * sg.cols + c0 + c;
+      const float4 v = in ? *reinterpret_cast<const float4*>(sg.src + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+      tile[r][c] = v.x; tile[r][c + 1] = v.y; tile[r][c + 2] = v.z; tile[r][c + 3] = v.w;
+      if (in) {
+        const uint2 h = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+        if (sg.copy) *reinterpret_cast<uint2*>(sg.copy + idx) = h;
+        if (sg.hi) {
+          *reinterpret_cast<uint2*>(sg.hi + idx) = h;
+          const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&h.x));
+          const float2 b2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&h.y));
+          *reinterpret_cast<uint2*>(sg.lo + idx) = make_uint2(pack_bf16(v.x - a.x, v.y - a.y), pack_bf16(v.z - b2.x, v.w - b2.y));
+        }
+      }
+    }
+    if (sg.trans == nullptr) return;
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+      const int c = i >> 4, r = (i & 15) * 4;
+      if (c0 + c < sg.cols && r0 + r < sg.rows)
+        *reinterpret_cast<uint2*>(sg.trans + static_cast<int64_t>(c0 + c) * sg.ld_trans + r0 + r) =
+            make_uint2(pack_bf16(tile[r][c], tile[r + 1][c]), pack_bf16(tile[r + 2][c], tile[r + 3][c]));
+    }
+    return;
+  }
   for (int i = threadIdx.x; i < 64 * 64; i += 256) {
     const int r = i >> 6, c = i & 63;
     const bool in = r0 + r < sg.rows && c0 + c < sg.cols;

@@ -536,3 +536,91 @@ def test_loss_curve_200_steps_dit_b_seq128_tracks_fp32_eager():
           f"L1 {win}-step window means within {l1_dev:.2e}, total-loss window medians within {med_dev:.2e}")
     assert float(rec["ref"][-1].mean()) < 0.97 * float(rec["ref"][0].mean())
     assert l1_dev < 1e-2 and med_dev < 1.5e-2  # L1 term within the north star's 1 %; the total's median is noisier at batch 32
+
+
+def test_batched_weight_repack_matches_per_tensor_casts():
+    """osudit_repack_weights: every bf16 / transposed / split copy the training step needs, from one launch, equals the
+    per-tensor casts (what autocast does per call in the reference, train.py:249-255); refreshed after an in-place update."""
+    import models
+    from osudit.train import TrainWeights
+    m = models.DiT(depth=2, hidden_size=384, num_heads=6, num_classes=100, context_size=144).to(DEV)
+    with torch.no_grad():
+        for p in m.parameters():
+            if p.requires_grad:
+                p.normal_(0, 0.3)
+    tw = TrainWeights().refresh(m)
+
+    def check():
+        def split_ok(pair, w):
+            hi, lo = pair
+            assert torch.equal(hi, bf(w))
+            assert torch.equal(lo, bf(w - bf(w).float()))
+
+        def trans_ok(t, w):
+            assert t.shape == (w.shape[1], (w.shape[0] + 7) // 8 * 8)
+            assert torch.equal(t[:, :w.shape[0]], bf(w).t()) and float(t[:, w.shape[0]:].abs().sum()) == 0.0
+
+        split_ok(tw.first_w, m.xoc_embedder.mlp[0].weight.detach())
+        split_ok(tw.t0_w, m.t_embedder.mlp[0].weight.detach())
+        split_ok(tw.t2_w, m.t_embedder.mlp[2].weight.detach())
+        trans_ok(tw.t2_wt, m.t_embedder.mlp[2].weight.detach())
+        mod = torch.cat([b.adaLN_modulation[1].weight.detach() for b in m.blocks] +
+                        [m.final_layer.adaLN_modulation[1].weight.detach()], 0)
+        split_ok(tw.mod_w, mod)
+        trans_ok(tw.mod_wt, mod)
+        assert torch.equal(tw.mod_b, torch.cat([b.adaLN_modulation[1].bias.detach() for b in m.blocks] +
+                                               [m.final_layer.adaLN_modulation[1].bias.detach()], 0))
+        for blk, d in zip(m.blocks, tw.blocks):
+            for name, w in (("qkv", blk.attn.in_proj_weight), ("out", blk.attn.out_proj.weight),
+                            ("fc1", blk.mlp.fc1.weight), ("fc2", blk.mlp.fc2.weight)):
+                assert torch.equal(d[name + "_w"], bf(w.detach()))
+                trans_ok(d[name + "_wt"], w.detach())
+
+    check()
+    table = tw._table.data_ptr()
+    with torch.no_grad():
+        m.blocks[1].mlp.fc1.weight.mul_(1.5)
+        m.final_layer.adaLN_modulation[1].weight.add_(0.25)
+    tw.refresh(m)
+    assert tw._table.data_ptr() == table  # same destinations, same table: only the launch is repeated
+    check()
+
+
+def test_replayed_gradients_survive_accumulation_and_in_place_zeroing():
+    """The captured training step hands autograd views of its static gradient buffers (adopted, not cloned).  Two
+    backward passes without zero_grad must still ADD (gradient accumulation) and zero_grad(set_to_none=False) must
+    still give the plain gradient next time.  (A reference to an old `.grad` that the caller keeps ACROSS steps after
+    zero_grad(set_to_none=True) aliases the replayed buffer; OSUDIT_CUDA_GRAPHS=0 gives private tensors.)"""
+    from diffusion import create_diffusion
+    from osudit import train as otrain
+    B, T = 4, 128
+    shape, sd, m, (x, o, c, y, noise, t) = _train_setup("DiT-S", B, T)
+    d = create_diffusion("", noise_schedule="squaredcos_cap_v2", use_l1=True)
+    kw = dict(o=o.to(DEV), c=c.to(DEV), y=y.to(DEV))
+    otrain._train_graphs.clear()
+
+    def backward(tt):
+        d.training_losses(m, x.to(DEV), tt.to(DEV), kw, noise=noise.to(DEV))["loss"].mean().backward()
+
+    t2 = (t + 7).clamp(max=999)
+    backward(t)   # captures
+    m.zero_grad(set_to_none=True)
+    backward(t)
+    g1 = {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
+    m.zero_grad(set_to_none=True)
+    backward(t2)
+    g2 = {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
+    assert rel(g2["blocks.0.mlp.fc1.weight"], g1["blocks.0.mlp.fc1.weight"]) > 1e-3  # the two steps do differ
+    # accumulation: t then t2 without zero_grad
+    m.zero_grad(set_to_none=True)
+    backward(t)
+    backward(t2)
+    worst = max(rel(p.grad, g1[k] + g2[k]) for k, p in m.named_parameters() if p.grad is not None)
+    assert worst < 1e-5, worst
+    # in-place zeroing
+    m.zero_grad(set_to_none=False)
+    backward(t)
+    worst = max(rel(p.grad, g1[k]) for k, p in m.named_parameters() if p.grad is not None)
+    assert worst < 1e-5, worst
+    assert len(otrain._train_graphs) == 1
+    otrain._train_graphs.clear()

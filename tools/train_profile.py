@@ -19,7 +19,13 @@ with torch.no_grad():
 model = model.to(dev).train()
 ema = deepcopy(model).requires_grad_(False)
 d = create_diffusion("", noise_schedule="squaredcos_cap_v2", use_l1=True)
-opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0)
+FUSED = os.environ.get("FUSED", "0") == "1"
+if FUSED:
+    from osudit.optim import FusedAdamWEMA
+    opt = FusedAdamWEMA(model.parameters(), lr=1e-4, weight_decay=0)
+    opt.attach_ema(ema, model, decay=0.9999)
+else:
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0)
 scaler = torch.amp.GradScaler("cuda")
 (x, o, c), y = synth.training_batch(B, 128, seed=0)
 x, o, c, y = [t.to(dev) for t in (x, o, c, y)]
@@ -35,7 +41,9 @@ def phases(sync):
     mark()
     scaler.scale(loss).backward(); mark()
     scaler.step(opt); scaler.update(); opt.zero_grad(set_to_none=True); mark()
-    bench_train.update_ema(ema, model); mark()
+    if not FUSED:
+        bench_train.update_ema(ema, model)
+    mark()
     return [b - a for a, b in zip(ts, ts[1:])]
 
 for _ in range(3): phases(True)
