@@ -647,7 +647,11 @@ extern "C" int osudit_attn_band(const void* qkv, void* out, int B, int T, int H,
     const char* e = getenv("OSUDIT_ATTN_FA");
     return !(e && e[0] == '0');
   }();
-  const bool long_band = window_ok && T > 256;
+  static const bool band_window = [] {  // OSUDIT_ATTN_BAND_WINDOW=0: the streaming kernel for the sampling band too
+    const char* e = getenv("OSUDIT_ATTN_BAND_WINDOW");
+    return !(e && e[0] == '0');
+  }();
+  const bool long_band = band_window && window_ok && T > 256;
   if (algo == OSUDIT_ATTN_FA || (algo == OSUDIT_ATTN_AUTO && fa_ok && prefer_fa && !long_band))
     return attn_fa_launch(qkv, out, B, T, H, w_left, w_right, lse, st);
   if (algo != OSUDIT_ATTN_MMA_SYNC && window_ok)

@@ -7,18 +7,20 @@
 // One CTA works on TWO 128-query tiles at a time ("slots"); each slot streams the 128-key slabs its tile may attend
 // (3 for the W = 128 band, T/128 for full attention, 1 for a 128-datapoint training window) through
 //     S = Q K_j^T (tcgen05, 128 TMEM columns)  ->  softmax warps: P_j = exp2(S * c - ref), bf16, to shared memory
-//     O += P_j V_j (tcgen05, 64 TMEM columns; V consumed as an MN-major B operand)
-// with an online softmax whose running reference is a lazily updated power of two: O and the running sum are
-// rescaled only when a row's scores outgrow the reference by more than 2^24 (an exact power-of-two factor, applied
-// to O in TMEM by the row's own thread), so the common path never touches O between slabs.  While one slot's softmax
-// warps exponentiate, the other slot's MMAs and TMEM hand-offs run: the tensor pipe, the MUFU unit and the TMEM read
-// port each see a steady stream instead of the serialised S -> softmax -> PV chain of a single tile.
+//     O_h += P_j[:, half h] V_j[half h] (tcgen05, 2 x 64 TMEM columns; V consumed as an MN-major B operand)
+// Two threads share a query row (64 of the slab's 128 keys each: 8 softmax warps per slot, 4 per scheduler with both
+// slots — a single warp per scheduler is latency-bound at ~900 cycles per 32-column chunk, tools/attn_fa_trace.py).
+// Each half keeps its OWN running reference and its OWN output accumulator, so the halves never synchronise inside a
+// tile; the epilogue combines them as (2^r0 O0 + 2^r1 O1) / (2^r0 s0 + 2^r1 s1).  The reference of a half is a lazily
+// updated power of two: O_h and the running sum are rescaled only when the scores outgrow it by more than 2^24 (an
+// exact power-of-two factor, applied to O_h in TMEM by the row's own thread), so the common path never touches O
+// between slabs.  While one slot's softmax warps exponentiate, the other slot's MMAs and TMEM hand-offs run.
 //
-//   warp 0 / 1   TMA producer of slot 0 / 1: Q tile, then K_j / V_j through two-stage rings (3-D tensor map over the
-//                packed qkv [B, T, 3D]; rows outside [0, T) are zero-filled per batch)
-//   warp 2 / 3   tcgen05.mma issuer of slot 0 / 1 (warp 2 also owns the TMEM allocation)
-//   warps 4-7    softmax + epilogue of slot 0, one thread per query row (TMEM lane quadrant = warp % 4)
-//   warps 8-11   same for slot 1
+//   warp 0 / 1    TMA producer of slot 0 / 1: Q tile, then K_j / V_j through two-stage rings (3-D tensor map over the
+//                 packed qkv [B, T, 3D]; rows outside [0, T) are zero-filled per batch)
+//   warp 2 / 3    tcgen05.mma issuer of slot 0 / 1 (warp 2 also owns the TMEM allocation)
+//   warps 4-11    softmax of slot 0: TMEM lane quadrant = warp % 4, key half = (warp - 4) / 4; half 1 runs the epilogue
+//   warps 12-19   same for slot 1
 // Optionally writes the log2-domain log-sum-exp of every row (the backward's input).
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -45,10 +47,11 @@ constexpr int kOffK = kOffQ + kTile;         // 2 stages
 constexpr int kOffV = kOffK + 2 * kTile;     // 2 stages
 constexpr int kOffP = kOffV + 2 * kTile;     // P[128][128] as 2 K-blocks of 64 keys
 constexpr int kSlot = kOffP + 2 * kTile;     // 112 KB per slot
-constexpr int kSmemBar = 2 * kSlot;
+constexpr int kSmemX = 2 * kSlot;              // [slot][row] (reference, sum) of half 0, handed to half 1's epilogue
+constexpr int kSmemBar = kSmemX + 2 * kQ * 8;
 constexpr int kBarsPerSlot = 13;
-constexpr int kSmemBytes = kSmemBar + 2 * kBarsPerSlot * 8 + 8 + 16 + 1024;
-constexpr int kThreads = 12 * 32;
+constexpr int kSmemBytes = kSmemBar + 2 * kBarsPerSlot * 8 + 8 + 16;  // 231.9 KB: no slack, the base is declared 1024-aligned
+constexpr int kThreads = 20 * 32;
 constexpr float kJump = 24.0f;               // see attn_window_tc.cu: P <= 2^24 before a re-reference
 
 struct Params {
@@ -144,9 +147,7 @@ __device__ long long g_fa_trace[2 * 2 * 32 * 8];
 #endif
 
 __global__ void __launch_bounds__(kThreads, 1) attn_fa_kernel(const __grid_constant__ Params p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bar_base = reinterpret_cast<uint64_t*>(smem + kSmemBar);
   uint64_t* stagger = bar_base + 2 * kBarsPerSlot;  // slot 0 finished its first slab: slot 1 may start
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_base + 2 * kBarsPerSlot + 1);
@@ -167,10 +168,10 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fa_kernel(const __grid_const
         mbar_init(&b.v_free[i], 1);
       }
       mbar_init(b.s_full, 1);
-      mbar_init(b.p_full, 4);  // one arrival per softmax warp
+      mbar_init(b.p_full, 8);  // one arrival per softmax warp
       mbar_init(b.pv_done, 1);
     }
-    mbar_init(stagger, 4);
+    mbar_init(stagger, 8);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -240,13 +241,13 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fa_kernel(const __grid_const
         mbar_wait(&bar.v_full[vs], (vn >> 1) & 1);
         tc_fence_after();
 #pragma unroll
-        for (int kb = 0; kb < 2; ++kb) {
+        for (int kb = 0; kb < 2; ++kb) {  // key half kb of the slab accumulates into its own O (own softmax reference)
           const uint64_t dp = desc_sw128(base + kOffP + kb * kTile);
           const uint64_t dv = desc_sw128(base + kOffV + vs * kTile + kb * (64 * 128));
 #pragma unroll
           for (int k = 0; k < 4; ++k)  // 16 keys: +32 B along P's row, +16 rows (2048 B) in V
-            umma_bf16(tmem_base + 2 * kS + s * kHD, dp + 2 * k, dv + 128 * k, idesc_o,
-                      (first && kb == 0 && k == 0) ? 0u : 1u);
+            umma_bf16(tmem_base + 2 * kS + (2 * s + kb) * kHD, dp + 2 * k, dv + 128 * k, idesc_o,
+                      (first && k == 0) ? 0u : 1u);
         }
         umma_commit(bar.pv_done);  // V is released by the softmax warps once they have seen pv_done
         ++vn;
@@ -267,173 +268,146 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fa_kernel(const __grid_const
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------ softmax + epilogue, one thread per query row
-    const int s = (warp - 4) >> 2;
+    // ------------------------------------------------- softmax + epilogue: two threads per query row (64 keys each)
+    const int s = (warp - 4) >> 3;
+    const int half = ((warp - 4) >> 2) & 1;
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
+    const bool lead = warp == 4 + 8 * s && lane == 0;  // releases the slot's K / V / Q buffers
     const Bars bar = slot_bars(bar_base, s);
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
-    const uint32_t col_s = s * kS, col_o = 2 * kS + s * kHD;
-    const uint32_t p_row = smem_u32(smem + s * kSlot + kOffP) + row * 128;  // shared-space address of this row of P
+    const uint32_t col_s = s * kS + half * 64, col_o = 2 * kS + (2 * s + half) * kHD;
+    const uint32_t p_row = smem_u32(smem + s * kSlot + kOffP) + half * kTile + row * 128;  // this thread's 64 keys of P
     const int swz = row & 7;
+    float2* xchg = reinterpret_cast<float2*>(smem + kSmemX) + s * kQ;
+    const uint32_t bar_a = 1 + 2 * s, bar_b = 2 + 2 * s;  // named barriers: half 0's (ref, sum) published / consumed
     uint32_t sn = 0;  // slab steps of this slot so far (parity of s_full / p_full / pv_done)
+    uint32_t tiles_done = 0;
     // The two slots must not run in lockstep (both exponentiating, then both waiting for the tensor pipe): slot 1
     // starts its first slab when slot 0 has finished its own, after which the slots alternate.
     if (s == 1 && 2 * static_cast<int>(blockIdx.x) + 1 < p.total_tiles) warp_mbar_wait(stagger, 0);
 
-    for (int tile = 2 * static_cast<int>(blockIdx.x) + s; tile < p.total_tiles; tile += 2 * G) {
+    for (int tile = 2 * static_cast<int>(blockIdx.x) + s; tile < p.total_tiles; tile += 2 * G, ++tiles_done) {
       const Tile t = decode_tile(p, tile);
       const int q = t.q0 + row;
-      float ref = -INFINITY;  // running reference (integer-valued, log2 domain)
+      float ref = -INFINITY;  // this half's running reference (integer-valued, log2 domain)
       float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
 
       for (int j = 0; j < t.n_slabs; ++j) {
-        const int k0 = (t.slab_lo + j) * kS;
-        // allowed columns of this row inside the slab, and the 32-column chunks any row of this warp needs
+        const int k0 = (t.slab_lo + j) * kS + half * 64;  // first key of this thread's 64 columns
+        // allowed columns of this row inside its 64, and the 32-column chunks any row of this warp needs
         const int c_lo = max(max(q - p.w_left, 0) - k0, 0);
-        const int c_hi = min(min(q + p.w_right, p.T - 1) - k0, kS - 1);
+        const int c_hi = min(min(q + p.w_right, p.T - 1) - k0, 63);
         const int w_lo = max(t.q0 + quad * 32 - p.w_left, 0) - k0;
         const int w_hi = min(t.q0 + quad * 32 + 31 + p.w_right, p.T - 1) - k0;
-        const int ch_lo = (w_hi >= 0 && w_lo < kS) ? (max(w_lo, 0) >> 5) : 4;
-        const int ch_hi = (w_hi >= 0 && w_lo < kS) ? (min(w_hi, kS - 1) >> 5) : -1;
-        auto in_range = [&](int c) { return c >= ch_lo && c <= ch_hi; };
-        float o_factor = 1.0f;  // what O (slabs 0..j-1) must be multiplied by before PV(j) accumulates onto it
-        bool pv_pending = false;
+        const int ch_lo = (w_hi >= 0 && w_lo < 64) ? (max(w_lo, 0) >> 5) : 2;
+        const int ch_hi = (w_hi >= 0 && w_lo < 64) ? (min(w_hi, 63) >> 5) : -1;
+        float o_factor = 1.0f;  // what O_h (slabs 0..j-1) must be multiplied by before PV(j) accumulates onto it
+        bool pv_pending = sn > 0;  // PV(sn-1) still reads P and V: awaited at the first store
 
-        auto store_chunk = [&](int c, const uint32_t(&packed)[16]) {
-          if (pv_pending) {  // first store of the slab (warp-uniform): P and V of the previous slab are still being read
-            warp_mbar_wait(bar.pv_done, (sn - 1) & 1);
-            if (warp == 4 + 4 * s && lane == 0) mbar_arrive(&bar.v_free[(sn - 1) & 1]);
-            pv_pending = false;
-          }
-          // 32 keys = 64 B = four 16-byte chunks of the 128-byte row in K-block c / 2
-          const uint32_t blk = p_row + (c >> 1) * kTile;
-#pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
-            const int chunk = (c & 1) * 4 + jj;
-            sts128(blk + ((chunk ^ swz) << 4), packed[4 * jj], packed[4 * jj + 1], packed[4 * jj + 2], packed[4 * jj + 3]);
-          }
-        };
-        // rare: the reference moved up by more than kJump: rescale what this thread already wrote for THIS slab
-        // (not yet published: p_full fires after the last chunk) and remember the factor for O
-        auto rescale_written = [&](int c_end, float factor) {
-          for (int cc = 0; cc < c_end; ++cc) {
-            const uint32_t blk = p_row + (cc >> 1) * kTile;
-            for (int jj = 0; jj < 4; ++jj) {
-              const int chunk = (cc & 1) * 4 + jj;
-              const uint32_t addr = blk + ((chunk ^ swz) << 4);
-              uint4 w = lds128(addr);
-              uint32_t* e = reinterpret_cast<uint32_t*>(&w);
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const float2 f = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&e[k]));
-                e[k] = pack_bf16(f.x * factor, f.y * factor);
-              }
-              sts128(addr, w.x, w.y, w.z, w.w);
-            }
-          }
-          sum0 *= factor; sum1 *= factor; sum2 *= factor; sum3 *= factor;
-          o_factor *= factor;
-        };
-        auto emit = [&](uint32_t(&v)[32], int c, bool tr = false) {
-          uint32_t packed[16];
-          if (!in_range(c)) {
-#pragma unroll
-            for (int k = 0; k < 16; ++k) packed[k] = 0u;
-            store_chunk(c, packed);
-            return;
-          }
-          const int base = c * 32;
-          if (!(base >= c_lo && base + 31 <= c_hi)) {  // boundary chunk: masked scores become -inf
-            const int klo = c_lo - base, khi = c_hi - base;
-#pragma unroll
-            for (int k = 0; k < 32; ++k)
-              if (k < klo || k > khi) v[k] = 0xff800000u;
-          }
-          if (ref == -INFINITY) {  // the row has not met an allowed key yet: its first chunk maximum is the reference
-            float m0 = -INFINITY, m1 = -INFINITY;
-#pragma unroll
-            for (int k = 0; k < 32; k += 2) {
-              m0 = fmaxf(m0, __uint_as_float(v[k]));
-              m1 = fmaxf(m1, __uint_as_float(v[k + 1]));
-            }
-            const float cm = fmaxf(m0, m1) * p.scale_log2;
-            if (cm > -INFINITY) ref = ceilf(cm);
-          }
-          // Common path: exponentiate against the current reference straight away and track the largest exponent on
-          // the side (off the MUFU stream's critical path); only if it exceeds kJump is the chunk redone.
-          float c0, c1, c2, c3;
-          auto exps = [&](float off) {
-            float a0 = -INFINITY, a1 = -INFINITY;
-            c0 = c1 = c2 = c3 = 0.f;
-#pragma unroll
-            for (int g = 0; g < 2; ++g) {  // two groups of 16 columns keep the live register set small
-              float pv[16];
-#pragma unroll
-              for (int k = 0; k < 16; ++k) {
-                const float a = fmaf(__uint_as_float(v[16 * g + k]), p.scale_log2, -off);
-#if defined(OSUDIT_FA_ABL) && OSUDIT_FA_ABL == 1  // ablation builds (tools/attn_fa_check.py --time): no MUFU
-                pv[k] = a * 0.001f;
-#else
-                pv[k] = fast_exp2(a);
-#endif
-                if (k & 1) a1 = fmaxf(a1, a); else a0 = fmaxf(a0, a);
-              }
-#if !(defined(OSUDIT_FA_ABL) && OSUDIT_FA_ABL == 2)  // ablation: no row sums
-#pragma unroll
-              for (int k = 0; k < 16; k += 4) {
-                c0 += pv[k];
-                c1 += pv[k + 1];
-                c2 += pv[k + 2];
-                c3 += pv[k + 3];
-              }
-#else
-              c0 += pv[0];
-#endif
-#pragma unroll
-              for (int k = 0; k < 8; ++k) packed[8 * g + k] = pack_bf16(pv[2 * k], pv[2 * k + 1]);
-            }
-            return fmaxf(a0, a1);
-          };
-          const float off = (ref == -INFINITY) ? 0.f : ref;
-          if (tr) FA_TRACE(s, 1, sn, 4);
-          const float amax = exps(off);
-          if (tr) FA_TRACE(s, 1, sn, 5);
-          if (amax > kJump) {  // rare: the scores outgrew the reference by more than 2^24: re-reference, redo
-            const float new_ref = ceilf(amax + off);
-            rescale_written(c, fast_exp2(ref - new_ref));
-            ref = new_ref;
-            exps(ref);
-          }
-          sum0 += c0; sum1 += c1; sum2 += c2; sum3 += c3;
-          store_chunk(c, packed);
-          if (tr) FA_TRACE(s, 1, sn, 6);
-        };
-
-        const bool tracer = quad == 0 && lane == 0;
+        const bool tracer = quad == 0 && lane == 0 && half == 0;
         if (tracer) FA_TRACE(s, 1, sn, 0);
         warp_mbar_wait_sleep(bar.s_full, sn & 1, 20);
         if (tracer) FA_TRACE(s, 1, sn, 1);
         tc_fence_after();
-        uint32_t ra[32], rb[32];
-        if (in_range(0)) FA_LD(t_lane + col_s, ra);
-        if (warp == 4 + 4 * s && lane == 0) {  // S(j) is complete: its K stage (and, after the last slab, Q) is free
+        if (lead) {  // S(j) is complete: its K stage (and, after the last slab, Q) is free
           mbar_arrive(&bar.k_free[sn & 1]);
           if (j + 1 == t.n_slabs) mbar_arrive(bar.q_free);
         }
-        pv_pending = j > 0;  // PV(j-1) must be complete before P is overwritten / O rescaled: awaited at the first store
-        if (tracer) FA_TRACE(s, 1, sn, 2);
-#pragma unroll 1  // keep the body (2 x emit) resident in the instruction cache
-        for (int u = 0; u < 4; u += 2) {
-          tmem_ld_wait();
-          if (tracer && u == 0) FA_TRACE(s, 1, sn, 3);
-          if (in_range(u + 1)) FA_LD(t_lane + col_s + (u + 1) * 32, rb);
-          emit(ra, u, tracer && u == 0);
-          tmem_ld_wait();
-          if (u + 2 < 4 && in_range(u + 2)) FA_LD(t_lane + col_s + (u + 2) * 32, ra);
-          emit(rb, u + 1);
+#pragma unroll 1  // one copy of the chunk body: the loop stays resident in the instruction cache
+        for (int c = 0; c < 2; ++c) {
+          uint32_t packed[16];
+          const bool live = c >= ch_lo && c <= ch_hi;
+          if (live) {
+            uint32_t v[32];
+            FA_LD(t_lane + col_s + c * 32, v);
+            tmem_ld_wait();
+            const int base = c * 32;
+            if (!(base >= c_lo && base + 31 <= c_hi)) {  // boundary chunk: masked scores become -inf
+              const int klo = c_lo - base, khi = c_hi - base;
+#pragma unroll
+              for (int k = 0; k < 32; ++k)
+                if (k < klo || k > khi) v[k] = 0xff800000u;
+            }
+            if (ref == -INFINITY) {  // no allowed key met yet: the first chunk maximum is the reference
+              float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+              for (int k = 0; k < 32; k += 2) {
+                m0 = fmaxf(m0, __uint_as_float(v[k]));
+                m1 = fmaxf(m1, __uint_as_float(v[k + 1]));
+              }
+              const float cm = fmaxf(m0, m1) * p.scale_log2;
+              if (cm > -INFINITY) ref = ceilf(cm);
+            }
+            // Common path: exponentiate against the current reference straight away and track the largest exponent
+            // on the side (off the MUFU stream's critical path); only if it exceeds kJump is the chunk redone.
+            float c0, c1, c2, c3;
+            auto exps = [&](float off) {
+              float a0 = -INFINITY, a1 = -INFINITY;
+              c0 = c1 = c2 = c3 = 0.f;
+#pragma unroll
+              for (int g = 0; g < 2; ++g) {  // two groups of 16 columns keep the live register set small
+                float pv[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                  const float a = fmaf(__uint_as_float(v[16 * g + k]), p.scale_log2, -off);
+#if defined(OSUDIT_FA_ABL) && OSUDIT_FA_ABL == 1  // ablation builds: no MUFU
+                  pv[k] = a * 0.001f;
+#else
+                  pv[k] = fast_exp2(a);
+#endif
+                  if (k & 1) a1 = fmaxf(a1, a); else a0 = fmaxf(a0, a);
+                }
+#pragma unroll
+                for (int k = 0; k < 16; k += 4) {
+                  c0 += pv[k];
+                  c1 += pv[k + 1];
+                  c2 += pv[k + 2];
+                  c3 += pv[k + 3];
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) packed[8 * g + k] = pack_bf16(pv[2 * k], pv[2 * k + 1]);
+              }
+              return fmaxf(a0, a1);
+            };
+            const float off = (ref == -INFINITY) ? 0.f : ref;
+            const float amax = exps(off);
+            if (amax > kJump) {  // rare: the scores outgrew the reference by more than 2^24: re-reference, redo
+              const float new_ref = ceilf(amax + off);
+              const float factor = fast_exp2(ref - new_ref);
+              if (c == 1) {  // rescale chunk 0 of this slab, written but not yet published
+                for (int jj = 0; jj < 4; ++jj) {
+                  const uint32_t addr = p_row + ((jj ^ swz) << 4);
+                  uint4 w = lds128(addr);
+                  uint32_t* e = reinterpret_cast<uint32_t*>(&w);
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    const float2 f = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&e[k]));
+                    e[k] = pack_bf16(f.x * factor, f.y * factor);
+                  }
+                  sts128(addr, w.x, w.y, w.z, w.w);
+                }
+              }
+              sum0 *= factor; sum1 *= factor; sum2 *= factor; sum3 *= factor;
+              o_factor *= factor;
+              ref = new_ref;
+              exps(ref);
+            }
+            sum0 += c0; sum1 += c1; sum2 += c2; sum3 += c3;
+          } else {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) packed[k] = 0u;
+          }
+          if (pv_pending) {  // first store of the slab (warp-uniform)
+            warp_mbar_wait(bar.pv_done, (sn - 1) & 1);
+            if (lead) mbar_arrive(&bar.v_free[(sn - 1) & 1]);
+            pv_pending = false;
+          }
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj)  // 32 keys = 64 B = four 16-byte pieces of the 128-byte row
+            sts128(p_row + (((c * 4 + jj) ^ swz) << 4), packed[4 * jj], packed[4 * jj + 1], packed[4 * jj + 2], packed[4 * jj + 3]);
         }
-        if (j > 0 && __any_sync(0xffffffffu, o_factor != 1.0f)) {
+        if (j > 0 && __any_sync(0xffffffffu, o_factor != 1.0f)) {  // rare: bring O_h down to the new reference
           tc_fence_after();
 #pragma unroll 1
           for (int hh = 0; hh < 2; ++hh) {
@@ -454,20 +428,37 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fa_kernel(const __grid_const
         ++sn;
       }
 
-      // ---- epilogue: O / sum -> bf16 -> global; log-sum-exp for the backward
-      warp_mbar_wait(bar.pv_done, (sn - 1) & 1);
-      if (warp == 4 + 4 * s && lane == 0) mbar_arrive(&bar.v_free[(sn - 1) & 1]);
-      tc_fence_after();
       const float sum = (sum0 + sum1) + (sum2 + sum3);
-      const float inv = 1.0f / sum;
+      if (half == 0) {
+        // hand (reference, sum) to the row's other thread and move on to the next tile
+        if (tiles_done > 0) named_bar_sync(bar_b, 256);  // half 1 has consumed the previous tile's values
+        xchg[row] = make_float2(ref, sum);
+        __threadfence_block();
+        asm volatile("bar.arrive %0, 256;" ::"r"(bar_a) : "memory");
+        continue;
+      }
+      // ---- epilogue (half 1): (w0 O0 + w1 O1) / (w0 s0 + w1 s1) -> bf16 -> global; log-sum-exp for the backward
+      named_bar_sync(bar_a, 256);
+      const float2 other = xchg[row];
+      asm volatile("bar.arrive %0, 256;" ::"r"(bar_b) : "memory");
+      warp_mbar_wait(bar.pv_done, (sn - 1) & 1);
+      tc_fence_after();
+      const float rmax = fmaxf(other.x, ref);
+      const float w_a = (other.x == -INFINITY) ? 0.f : fast_exp2(other.x - rmax);
+      const float w_b = (ref == -INFINITY) ? 0.f : fast_exp2(ref - rmax);
+      const float total = w_a * other.y + w_b * sum;
+      const float inv = 1.0f / total;
+      const float ka = w_a * inv, kb = w_b * inv;
       uint4* dst = reinterpret_cast<uint4*>(p.out + (static_cast<int64_t>(t.b) * p.T + q) * p.D + t.h * kHD);
+      const uint32_t col_o0 = 2 * kS + 2 * s * kHD;
 #pragma unroll 1
-      for (int hh = 0; hh < 2; ++hh) {
-        uint32_t o[32];
-        tmem_ld_32x32(t_lane + col_o + hh * 32, o);
+      for (int hh = 0; hh < 2; ++hh) {  // two groups of 32 head dims
+        uint32_t o0[32], o1[32];
+        tmem_ld_32x32(t_lane + col_o0 + hh * 32, o0);
+        tmem_ld_32x32(t_lane + col_o0 + kHD + hh * 32, o1);
         tmem_ld_wait();
         if (q < p.T) {
-          auto f = [&](int k) { return __uint_as_float(o[k]) * inv; };
+          auto f = [&](int k) { return fmaf(__uint_as_float(o0[k]), ka, __uint_as_float(o1[k]) * kb); };
 #pragma unroll
           for (int jj = 0; jj < 4; ++jj)
             dst[hh * 4 + jj] =
@@ -476,7 +467,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fa_kernel(const __grid_const
         }
       }
       if (p.lse != nullptr && q < p.T)
-        p.lse[(static_cast<int64_t>(t.b) * p.H + t.h) * p.T + q] = ref + log2f(sum);
+        p.lse[(static_cast<int64_t>(t.b) * p.H + t.h) * p.T + q] = rmax + log2f(total);
       tc_fence_before();  // the O reads above are ordered before this thread's next p_full arrival
     }
   }
