@@ -74,9 +74,13 @@ def workload_config(n_gpus):
             "l2_policy": "inputs and activations (>5 GB per step) exceed the 126 MB L2; no flush needed"}
 
 
+SIZES = {"DiT-S": (384, 12, 6), "DiT-B": (768, 12, 12), "DiT-L": (1024, 24, 16), "DiT-XL": (1152, 28, 16)}
+
+
 def flops_per_beatmap():
     """Algorithmic flop count, attention over the +-128 band only."""
-    D, depth, H, hd = 768, 12, 12, 64
+    D, depth, H = SIZES[MODEL]
+    hd = D // H
     gemm_tok = 24 * D * D * depth + 2 * 528 * D + 2 * D * 4
     pairs = sum(min(SEQ - 1, j + BAND) - max(0, j - (BAND - 1)) + 1 for j in range(SEQ))
     attn_row = pairs * 4 * hd * H * depth
@@ -206,8 +210,11 @@ def run_native(args, rank, world, local_rank):
         ms = timed(sample_resident, args.steps)
         launches = ops.launch_count - l0
         clk = clocks.stop() if rank == 0 else None
-        sample_e2e()
-        ms_e2e = timed(sample_e2e, args.steps)
+        if args.no_e2e:
+            ms_e2e = None
+        else:
+            sample_e2e()
+            ms_e2e = timed(sample_e2e, args.steps)
         roof = kernel_roofline(model, diffusion, zd, od, cd, yd, mask_d, device) if rank == 0 else None
 
     total = N_BEATMAPS * world * args.steps
@@ -227,15 +234,16 @@ def run_native(args, rank, world, local_rank):
         "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": workload_config(world), "clocks": clk,
-        "e2e": {"value": round(total / (ms_e2e / 1e3), 4), "unit": UNIT,
-                "h2d_bytes_per_step": sum(t.numel() * t.element_size() for t in host),
-                "d2h_bytes_per_step": out_host.numel() * out_host.element_size()},
+        "e2e": None if ms_e2e is None else {
+            "value": round(total / (ms_e2e / 1e3), 4), "unit": UNIT,
+            "h2d_bytes_per_step": sum(t.numel() * t.element_size() for t in host),
+            "d2h_bytes_per_step": out_host.numel() * out_host.element_size()},
         "gpu_launches": launches,
         "model_tflops": round(flops_per_beatmap() * value / world / 1e12, 1),
         "roofline": roof,
         "train": train,
     }
-    line["cpu_baseline"] = cpu_baseline_sample() if world == 1 else None
+    line["cpu_baseline"] = cpu_baseline_sample() if (world == 1 and not args.no_cpu_baseline) else None
     if dist is not None:
         dist.destroy_process_group()
     return line
@@ -254,7 +262,7 @@ def run_train(rank, world, local_rank, dist, device, steps=20, warmup=8):
     """BASELINE config 3 through the drop-in API: train.py:243-261's step (label dropout, t ~ U{0..999},
     `training_losses` under fp16 autocast, GradScaler, AdamW 1e-4, EMA 0.9999) on synthetic windows, DDP over the
     ranks.  Two variants are timed: "stock" = train.py's own optimizer / EMA loop / DistributedDataParallel call,
-    and the headline = the documented opt-ins (osudit.optim.FusedAdamWEMA, osudit.ddp.wrap: bf16 buckets, bucket
+    and the headline = the documented opt-ins (osudit.optim.FusedAdamWEMA, osudit.ddp.wrap: 128 MB buckets as bucket
     views, SMs reserved for NCCL).  `allreduce_ms_exposed` = step time minus the same step under `no_sync()`."""
     import contextlib
     from copy import deepcopy
@@ -349,7 +357,7 @@ def run_train(rank, world, local_rank, dist, device, steps=20, warmup=8):
     tf_peak = json.load(open(pk_path))["bf16_tflops_sustained"] if os.path.exists(pk_path) else 1400.0
     value = TRAIN_GLOBAL_BATCH / (ms_f / 1e3)
     tfl = train_flops_per_seq() * value / world / 1e12
-    bytes_ar = nparam * 2
+    bytes_ar = nparam * 4
     return {
         "metric": f"train seq/s {TRAIN_MODEL} seq-len {TRAIN_SEQ}", "value": round(value, 1), "unit": "seq/s",
         "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": round(ms_f, 3), "scaling": "strong",
@@ -358,12 +366,12 @@ def run_train(rank, world, local_rank, dist, device, steps=20, warmup=8):
         "config": {"workload": f"{TRAIN_MODEL} training, seq-len {TRAIN_SEQ}, global batch {TRAIN_GLOBAL_BATCH}, L1+VB loss, "
                                "AdamW 1e-4, EMA, fp16-autocast context + GradScaler as train.py:243-261",
                    "optimizer": "osudit.optim.FusedAdamWEMA (opt-in: AdamW + EMA + unscale in one launch)",
-                   "parallelism": f"dp{world}: DistributedDataParallel over NCCL via osudit.ddp.wrap (bf16 gradient buckets, "
-                                  "bucket views, 16 SMs reserved for NCCL)" if world > 1 else "dp1 (no collective)"},
+                   "parallelism": f"dp{world}: DistributedDataParallel over NCCL via osudit.ddp.wrap (fp32 gradient buckets of "
+                                  "128 MB as bucket views, 16 SMs reserved for NCCL)" if world > 1 else "dp1 (no collective)"},
         "allreduce_ms_exposed": round(ms_f - ns_f, 3) if world > 1 else 0.0,
         "collective": None if world == 1 else {
             "op": "NCCL all-reduce of the parameter gradients (train.py:152,257), the only collective on the path",
-            "bytes_per_step": bytes_ar, "dtype": "bf16 buckets",
+            "bytes_per_step": bytes_ar, "dtype": "fp32 buckets",
             "floor_ms_at_725GBs_busbw": round(bytes_ar * 2 * (world - 1) / world / 725e9 * 1e3, 3)},
         "roofline": {"bound": "tensor", "achieved": round(tfl, 1), "peak": tf_peak, "unit": "TFLOP/s (model-level, per GPU)",
                      "frac": round(tfl / tf_peak, 4)},
@@ -413,7 +421,7 @@ def kernel_roofline(model, diffusion, zd, od, cd, yd, mask_d, device):
     from osudit import graphs
     graphs_on, graphs._ENABLED = graphs._ENABLED, False  # per-launch events need the individual launches
     try:
-        t = torch.full((zd.shape[0],), 50, device=device, dtype=torch.long)
+        t = torch.full((zd.shape[0],), diffusion.num_timesteps // 2, device=device, dtype=torch.long)
         for _ in range(3):
             diffusion.p_sample(model.forward_with_cfg, zd, t, clip_denoised=True,
                                model_kwargs=dict(o=od, c=cd, y=yd, cfg_scale=CFG, attn_mask=mask_d))
@@ -454,7 +462,8 @@ def kernel_roofline(model, diffusion, zd, od, cd, yd, mask_d, device):
                            "achieved": round(lb / (lms / 1e3) / 1e9, 1), "peak": hbm_peak, "unit": "GB/s",
                            "frac": round(lb / (lms / 1e3) / 1e9 / hbm_peak, 4), "launches_timed": ln_n,
                            "share_of_step": round(lms / step_ms, 3)},
-            "attention_kernel": {"kernel": "attn_tc::attn_window_kernel", "achieved": round(af / (ams / 1e3) / 1e12, 1),
+            "attention_kernel": {"kernel": "attn_tc::attn_window_kernel" if SIZES[MODEL][0] // SIZES[MODEL][2] == 64
+                                 else "attn_band_kernel<72> (mma.sync)", "achieved": round(af / (ams / 1e3) / 1e12, 1),
                                  "unit": "TFLOP/s (banded algorithmic flops)", "share_of_step": round(ams / step_ms, 3)}}
 
 
@@ -651,7 +660,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-train", action="store_true", help="skip the training arm (the \"train\" record)")
+    ap.add_argument("--model", default=MODEL, choices=sorted(SIZES),
+                    help="sampling model (default: the headline DiT-B; DiT-XL + --diffusion-steps 1000 = BASELINE config 4)")
+    ap.add_argument("--diffusion-steps", type=int, default=STEPS_DIFF)
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU reference sample (non-default workloads)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (long non-default workloads only)")
     args = ap.parse_args()
+    globals().update(MODEL=args.model, STEPS_DIFF=args.diffusion_steps)
+    if (args.model, args.diffusion_steps) != ("DiT-B", 100):
+        globals().update(METRIC=f"beatmaps/sec {args.model} {args.diffusion_steps}-step CFG sampling")
     # stdout carries exactly ONE JSON line: keep the real stdout aside and point fd 1 at stderr, so that anything a
     # library writes to C stdout (NCCL prints its version banner there when NCCL_DEBUG is set) cannot precede it
     sys.stdout.flush()

@@ -63,7 +63,11 @@ def run_native(args, rank, world, local_rank):
     ema = deepcopy(model).requires_grad_(False)
     net = model
     if world > 1:
-        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank])
+        if args.fused_optimizer:  # the documented opt-ins: bf16 buckets, bucket views, SMs reserved for NCCL
+            from osudit import ddp
+            net = ddp.wrap(model, device_ids=[local_rank])
+        else:
+            net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank])  # train.py:152
     diffusion = create_diffusion("", noise_schedule="squaredcos_cap_v2", use_l1=True)
     if args.fused_optimizer:  # opt-in: AdamW + EMA + unscale + inf-skip in one launch (osudit/optim.py)
         from osudit.optim import FusedAdamWEMA
