@@ -291,7 +291,6 @@ def run_train(rank, world, local_rank, dist, device, steps=20, warmup=8):
             if fused:
                 net = ddp.wrap(m, device_ids=[local_rank])
             else:
-                ddp.set_sm_limit(0)
                 net = torch.nn.parallel.DistributedDataParallel(m, device_ids=[local_rank])  # train.py:152
         if fused:
             opt = FusedAdamWEMA(net.parameters(), lr=1e-4, weight_decay=0)

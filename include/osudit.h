@@ -28,7 +28,7 @@ extern "C" {
 int osudit_version(void); /* library ABI version (no reference counterpart: the reference has no FFI) */
 
 /* Caps the grid of every persistent kernel (GEMMs, windowed attention) at `n` CTAs instead of one per SM (0 = no cap;
- * rounded down to an even number for the CTA-pair GEMM); returns the previous cap.  Data-parallel training sets it so
+ * rounded down to an even number for the CTA-pair GEMM; n = -1 only queries); returns the previous cap.  Data-parallel training sets it so
  * that NCCL's all-reduce kernels (train.py:152,257) find free SMs next to the backward instead of queueing behind a
  * full-machine persistent grid.  Process-wide; takes effect at the next launch (captured graphs keep their grids). */
 int osudit_set_sm_limit(int n);

@@ -39,7 +39,8 @@ int num_sms() {
 extern "C" const char* osudit_last_error(void) { return osudit::g_err; }
 extern "C" int osudit_version(void) { return OSUDIT_VERSION; }
 extern "C" int osudit_set_sm_limit(int n) {
-  if (n < 0) return osudit::set_error(-1, "set_sm_limit: negative limit");
+  if (n == -1) return osudit::g_sm_limit;  // query
+  if (n < 0) return osudit::set_error(-2, "set_sm_limit: negative limit");
   const int prev = osudit::g_sm_limit;
   osudit::g_sm_limit = n & ~1;  // CTA pairs: keep it even
   return prev;

@@ -597,9 +597,25 @@ class _FinalFn(torch.autograd.Function):
         return (g, None) + tuple(grads)
 
 
+def _reserve_sms_for_nccl():
+    """Data-parallel training (train.py:152): NCCL's all-reduce kernels run beside the backward, but a persistent
+    GEMM grid that fills all 148 SMs leaves them no room and the step time doubles (measured, osudit/ddp.py).  A
+    training forward in a multi-rank process therefore caps the persistent grids when nobody has (16 SMs stay free;
+    OSUDIT_DDP_RESERVE_SMS overrides, 0 disables) — also for an unmodified train.py that never calls osudit.ddp.wrap."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return
+    reserve = int(os.environ.get("OSUDIT_DDP_RESERVE_SMS", "16"))
+    lib = ops._lib.load()
+    if reserve > 0 and lib.osudit_set_sm_limit(-1) == 0:
+        sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+        lib.osudit_set_sm_limit(max(sms - reserve, sms // 2))
+
+
 def dit_forward_train(model, tw, x, t, o, c, y, attn_mask):
     """out = DiT(x, t, o, c, y) as a chain of autograd nodes over one native forward: head -> block 0 -> ... ->
     block L-1 -> final.  Autograd walks it backwards, so parameter gradients are released group by group."""
+    _reserve_sms_for_nccl()
     call = _Call()
     call.model, call.tw, call.graph, call.S, call.bs, call.carry = model, tw, None, None, None, None
     head, blocks, final = param_groups(model)
