@@ -60,6 +60,7 @@ int osudit_gemm_bf16(int nseg, const void* const* a, const int64_t* lda, const v
 #define OSUDIT_ATTN_MMA_SYNC 1
 #define OSUDIT_ATTN_TCGEN05 2
 #define OSUDIT_ATTN_FA 3
+#define OSUDIT_ATTN_STREAM 4
 /* FA: the streaming tcgen05 kernel (attn_fa.cu): two 128-query tiles in flight per CTA, 128-key slabs, online
  * softmax with S and O in TMEM; head_dim 64, any T, band or full, optional lse.  AUTO prefers it where it applies.
  * lse (optional, fp32 [B, H, T]): log2-domain log-sum-exp of every row, saved for the backward. */

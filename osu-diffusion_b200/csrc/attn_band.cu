@@ -616,6 +616,9 @@ int attn_bwd_tc_launch(const void* qkv, const void* out, const void* dout, const
 bool attn_fa_applicable(int head_dim, const uint8_t* mask);
 int attn_fa_launch(const void* qkv, void* out, int B, int T, int H, int w_left, int w_right, float* lse,
                    cudaStream_t stream);
+bool attn_stream_applicable(int head_dim, const uint8_t* mask);
+int attn_stream_launch(const void* qkv, void* out, int B, int T, int H, int w_left, int w_right, float* lse,
+                       cudaStream_t stream);
 
 }  // namespace osudit
 
@@ -652,6 +655,14 @@ extern "C" int osudit_attn_band(const void* qkv, void* out, int B, int T, int H,
     return !(e && e[0] == '0');
   }();
   const bool long_band = band_window && window_ok && T > 256;
+  static const int stream_mode = [] {  // OSUDIT_ATTN_STREAM=1: the double-buffered streaming kernel wherever it applies
+    const char* e = getenv("OSUDIT_ATTN_STREAM");
+    return e ? atoi(e) : 0;
+  }();
+  if (algo == OSUDIT_ATTN_STREAM && !fa_ok)
+    return set_error(-1, "attn_band: the streaming tcgen05 kernel needs head_dim 64 and no generic mask");
+  if (algo == OSUDIT_ATTN_STREAM || (algo == OSUDIT_ATTN_AUTO && fa_ok && stream_mode == 1))
+    return attn_stream_launch(qkv, out, B, T, H, w_left, w_right, lse, st);
   if (algo == OSUDIT_ATTN_FA || (algo == OSUDIT_ATTN_AUTO && fa_ok && prefer_fa && !long_band))
     return attn_fa_launch(qkv, out, B, T, H, w_left, w_right, lse, st);
   if (algo != OSUDIT_ATTN_MMA_SYNC && window_ok)

@@ -74,7 +74,7 @@ def gemm_aux(a, w, bias, epilogue: int, out, aux):
     return out
 
 
-ATTN_AUTO, ATTN_MMA_SYNC, ATTN_TCGEN05, ATTN_FA = 0, 1, 2, 3
+ATTN_AUTO, ATTN_MMA_SYNC, ATTN_TCGEN05, ATTN_FA, ATTN_STREAM = 0, 1, 2, 3, 4
 
 
 def attn_band(qkv, out, B, T, H, head_dim, w_left=-1, w_right=-1, mask=None, algo=ATTN_AUTO, lse=None):

@@ -11,6 +11,7 @@ import torch
 from osudit import ops
 
 DEV = "cuda"
+ALGO = ops.ATTN_STREAM if "--stream" in sys.argv else ops.ATTN_FA
 
 
 def reference(qkv, B, T, H, hd, wl, wr):
@@ -41,7 +42,7 @@ def check(B, T, H, wl, wr, scale=1.0, ramp=0.0, seed=0):
     qkv = qkv.to(torch.bfloat16)
     out = torch.full((B * T, H * hd), float("nan"), device=DEV, dtype=torch.bfloat16)
     lse = torch.full((B, H, T), float("nan"), device=DEV)
-    ops.attn_band(qkv, out, B, T, H, hd, wl, wr, None, ops.ATTN_FA, lse=lse)
+    ops.attn_band(qkv, out, B, T, H, hd, wl, wr, None, ALGO, lse=lse)
     torch.cuda.synchronize()
     ref, lse_ref = reference(qkv, B, T, H, hd, wl, wr)
     e_o, e_l = rel(out.float(), ref), float((lse - lse_ref).abs().max())
@@ -82,7 +83,7 @@ if __name__ == "__main__":
             out = torch.empty(B * T, H * hd, device=DEV, dtype=torch.bfloat16)
             lse = torch.empty(B, H, T, device=DEV)
             res = {}
-            for tag, algo, l in [("fa", ops.ATTN_FA, None), ("fa+lse", ops.ATTN_FA, lse), ("mma.sync+lse", ops.ATTN_MMA_SYNC, lse)] + \
+            for tag, algo, l in [("stream", ops.ATTN_STREAM, None), ("stream+lse", ops.ATTN_STREAM, lse), ("fa", ops.ATTN_FA, None), ("fa+lse", ops.ATTN_FA, lse), ("mma.sync+lse", ops.ATTN_MMA_SYNC, lse)] + \
                     ([("window", ops.ATTN_TCGEN05, None)] if (wl >= 0 or T <= 256) else []):
                 res[tag] = timeit(lambda: ops.attn_band(qkv, out, B, T, H, hd, wl, wr, None, algo, lse=l))
             pairs = sum(min(T - 1, j + (wr if wr >= 0 else T)) - max(0, j - (wl if wl >= 0 else T)) + 1 for j in range(T))
