@@ -61,8 +61,10 @@ int osudit_gemm_bf16(int nseg, const void* const* a, const int64_t* lda, const v
 #define OSUDIT_ATTN_TCGEN05 2
 #define OSUDIT_ATTN_FA 3
 #define OSUDIT_ATTN_STREAM 4
-/* FA: the streaming tcgen05 kernel (attn_fa.cu): two 128-query tiles in flight per CTA, 128-key slabs, online
- * softmax with S and O in TMEM; head_dim 64, any T, band or full, optional lse.  AUTO prefers it where it applies.
+/* STREAM: the double-buffered streaming tcgen05 kernel (attn_stream.cu): 128-key slabs, scores two slabs ahead of
+ * the softmax in three TMEM buffers, probabilities written back to TMEM (PV reads its A operand there), epilogue
+ * warps with a TMA store; head_dim 64, any T, band or full, optional lse.  AUTO prefers it where it applies.
+ * FA: the two-slot streaming kernel (attn_fa.cu), same coverage (round 2a; kept selectable).
  * lse (optional, fp32 [B, H, T]): log2-domain log-sum-exp of every row, saved for the backward. */
 int osudit_attn_band(const void* qkv, void* out, int B, int T, int H, int head_dim, int w_left,
                      int w_right, const uint8_t* mask, int algo, float* lse, void* stream);

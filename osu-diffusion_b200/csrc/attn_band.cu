@@ -643,26 +643,28 @@ extern "C" int osudit_attn_band(const void* qkv, void* out, int B, int T, int H,
   const bool fa_ok = attn_fa_applicable(head_dim, mask);
   if (algo == OSUDIT_ATTN_FA && !fa_ok)
     return set_error(-1, "attn_band: the streaming tcgen05 kernel needs head_dim 64 and no generic mask");
-  // AUTO: the streaming two-tile kernel wherever it applies (any T, band or full, with or without lse), except the
-  // long-sequence narrow band of sampling, where the single-pass window kernel is still ~10 % faster (0.73 vs 0.82 ms
-  // per DiT-B layer at 128 x 2048); OSUDIT_ATTN_FA=0 restores the round-1 choice (window kernel / mma.sync)
+  // AUTO, head_dim 64 without a generic mask: the double-buffered streaming kernel (attn_stream.cu) for every shape —
+  // 0.60 ms per DiT-B layer on the sampling band (window kernel 0.73, two-slot kernel 0.73), 0.047 ms on 256 training
+  // windows of 128 (two-slot 0.056), 0.307 ms at 128 x 512 x 16 heads (0.310).  The older tcgen05 kernels stay
+  // selectable: OSUDIT_ATTN_STREAM=0 restores the round-2a choice (two-slot kernel, window kernel for the long band),
+  // additionally OSUDIT_ATTN_FA=0 the round-1 choice (window kernel / mma.sync).
+  static const bool prefer_stream = [] {
+    const char* e = getenv("OSUDIT_ATTN_STREAM");
+    return !(e && e[0] == '0');
+  }();
   static const bool prefer_fa = [] {
     const char* e = getenv("OSUDIT_ATTN_FA");
     return !(e && e[0] == '0');
   }();
-  static const bool band_window = [] {  // OSUDIT_ATTN_BAND_WINDOW=0: the streaming kernel for the sampling band too
+  static const bool band_window = [] {  // OSUDIT_ATTN_BAND_WINDOW=0: the two-slot kernel for the sampling band too
     const char* e = getenv("OSUDIT_ATTN_BAND_WINDOW");
     return !(e && e[0] == '0');
   }();
-  const bool long_band = band_window && window_ok && T > 256;
-  static const int stream_mode = [] {  // OSUDIT_ATTN_STREAM=1: the double-buffered streaming kernel wherever it applies
-    const char* e = getenv("OSUDIT_ATTN_STREAM");
-    return e ? atoi(e) : 0;
-  }();
   if (algo == OSUDIT_ATTN_STREAM && !fa_ok)
     return set_error(-1, "attn_band: the streaming tcgen05 kernel needs head_dim 64 and no generic mask");
-  if (algo == OSUDIT_ATTN_STREAM || (algo == OSUDIT_ATTN_AUTO && fa_ok && stream_mode == 1))
+  if (algo == OSUDIT_ATTN_STREAM || (algo == OSUDIT_ATTN_AUTO && fa_ok && prefer_stream))
     return attn_stream_launch(qkv, out, B, T, H, w_left, w_right, lse, st);
+  const bool long_band = band_window && window_ok && T > 256;
   if (algo == OSUDIT_ATTN_FA || (algo == OSUDIT_ATTN_AUTO && fa_ok && prefer_fa && !long_band))
     return attn_fa_launch(qkv, out, B, T, H, w_left, w_right, lse, st);
   if (algo != OSUDIT_ATTN_MMA_SYNC && window_ok)

@@ -48,6 +48,22 @@ int make_tensor_map_3d(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t 
 
 namespace attn_st {
 
+#ifndef ST_DEFER
+#define ST_DEFER 0
+#endif
+#ifndef ST_EARLYPROBE
+#define ST_EARLYPROBE 1
+#endif
+#ifndef ST_PWAIT
+#define ST_PWAIT 0
+#endif
+#ifndef ST_ABL
+#define ST_ABL 0
+#endif
+#ifndef ST_EPI_EARLY
+#define ST_EPI_EARLY 0
+#endif
+
 constexpr int kQ = 128;                      // queries per tile
 constexpr int kS = 128;                      // keys per slab
 constexpr int kHD = 64;
@@ -168,7 +184,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_stream_kernel(const __grid_c
   uint64_t* k_full = q_free + kQStages;            // [kKStages]
   uint64_t* k_free = k_full + kKStages;
   uint64_t* v_full = k_free + kKStages;            // [kVStages]
-  uint64_t* v_free = v_full + kVStages;            //   PV(n) complete (tcgen05.commit): V(n) is free, O_h holds slab n
+  uint64_t* v_free = v_full + kVStages;
   uint64_t* s_full = v_free + kVStages;            // [kSBufs] S(n) complete in TMEM buffer n % kSBufs
   uint64_t* p_full = s_full + kSBufs;              // [kSBufs] P(n) written back into that buffer (8 warp arrivals)
   uint64_t* o_full = p_full + kSBufs;              // every PV of a tile complete: O final
@@ -261,31 +277,28 @@ __global__ void __launch_bounds__(kThreads, 1) attn_stream_kernel(const __grid_c
       const uint64_t dk0 = desc_sw128(sbase + kQStages * kTile);
       const uint64_t dv0 = desc_sw128(sbase + (kQStages + kKStages) * kTile);
       constexpr uint32_t kStageStep = kTile >> 4;
-      // a barrier that is normally complete by the time it is asked for: probe without a sleep first
-      auto wait_ready = [&](uint64_t* bar, uint32_t parity) {
-        if (lane == 0) {
-          while (!mbar_try_wait(bar, parity)) __nanosleep(20);
-        }
-        __syncwarp();
+      // A barrier probe is a round trip through the memory-instruction queue (~200 cycles even on success, more
+      // while the softmax warps of this scheduler keep that queue full of MUFU work), and so is a tcgen05.commit; the
+      // warp's service time per slab, not the tensor pipe, bounded the kernel (tools/attn_stream_trace.py).  So: the
+      // barriers that are normally complete (V, K, Q, O free) are probed BEFORE the wait for P, their answers are
+      // used after it; and there is ONE commit per slab: PV(n) and S(n+3) are issued together, S(n+3)'s completion
+      // (the tensor pipe runs in issue order) doubles as "PV(n) done" for the V ring and the softmax warps.
+      auto probe = [&](uint64_t* bar, uint32_t parity) { return lane != 0 || mbar_try_wait(bar, parity); };
+      auto ensure = [&](bool ok, uint64_t* bar, uint32_t parity) {
+        if (!ok) mbar_wait_sleep(bar, parity, 20);  // lane 0 only
       };
-      // S cursor
+      // S cursor: the slab whose scores are issued next (three ahead of the PV cursor)
       int tile_s = blockIdx.x, j_s = 0, ns_s = decode_tile(p, tile_s).n_slabs;
       Ring rq, rk, rs_s;
-      auto issue_s = [&]() {
-        if (j_s == 0) wait_ready(&q_full[rq.stage], rq.phase);
-        wait_ready(&k_full[rk.stage], rk.phase);
-        tc_fence_after();
+      auto s_mmas = [&]() {  // elected lane
         const uint64_t dq = dq0 + static_cast<uint32_t>(rq.stage) * kStageStep;
         const uint64_t dk = dk0 + static_cast<uint32_t>(rk.stage) * kStageStep;
-        if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kHD / 16; ++k)
-            umma_bf16(tb + rs_s.stage * kS, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
-          umma_commit(&s_full[rs_s.stage]);
-        }
-        __syncwarp();
+        for (int k = 0; k < kHD / 16; ++k)
+          umma_bf16(tb + rs_s.stage * kS, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+      };
+      auto s_advance = [&]() {
         rk.advance(kKStages);
-        rs_s.advance(kSBufs);
         if (++j_s == ns_s) {
           j_s = 0;
           tile_s += G;
@@ -293,24 +306,60 @@ __global__ void __launch_bounds__(kThreads, 1) attn_stream_kernel(const __grid_c
           if (tile_s < p.total_tiles) ns_s = decode_tile(p, tile_s).n_slabs;
         }
       };
-      for (int i = 0; i < kSBufs; ++i)
-        if (tile_s < p.total_tiles) issue_s();
+      for (int i = 0; i < kSBufs; ++i) {
+        if (tile_s < p.total_tiles) {
+          if (lane == 0) {
+            if (j_s == 0) mbar_wait_sleep(&q_full[rq.stage], rq.phase, 20);
+            mbar_wait_sleep(&k_full[rk.stage], rk.phase, 20);
+          }
+          __syncwarp();
+          tc_fence_after();
+          if (elect_one()) {
+            s_mmas();
+            umma_commit(&s_full[rs_s.stage]);
+          }
+          __syncwarp();
+          s_advance();
+          rs_s.advance(kSBufs);
+        }
+      }
       uint32_t n = 0, tn = 0;
       Ring rv, rs;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += G, ++tn) {
         const int ns = decode_tile(p, tile).n_slabs;
         constexpr uint32_t col_o = kSBufs * kS;
         for (int j = 0; j < ns; ++j, ++n) {
-          if (lane == 0) ST_TRACE(0, n, 0);
-          warp_mbar_wait_sleep(&p_full[rs.stage], rs.phase, 32);
-          if (lane == 0) ST_TRACE(0, n, 1);
-          if (j == 0 && tn >= 1) wait_ready(o_free, (tn - 1) & 1);  // the epilogue has read the previous tile's O
-          wait_ready(&v_full[rv.stage], rv.phase);
+          const bool s_valid = tile_s < p.total_tiles;
+          const bool ok_v = probe(&v_full[rv.stage], rv.phase);
+          const bool ok_k = !s_valid || probe(&k_full[rk.stage], rk.phase);
+          const bool ok_q = !(s_valid && j_s == 0) || probe(&q_full[rq.stage], rq.phase);
+          const bool ok_o = !(j == 0 && tn >= 1) || probe(o_free, (tn - 1) & 1);  // the epilogue has read the previous O
+#if ST_PWAIT == 2  // every lane probes: no divergent region around the wait
+          while (!mbar_try_wait(&p_full[rs.stage], rs.phase)) {
+          }
+#endif
+          if (lane == 0) {
+            ST_TRACE(0, n, 0);
+#if ST_PWAIT == 1
+            mbar_wait(&p_full[rs.stage], rs.phase);
+#elif ST_PWAIT == 0
+            mbar_wait_sleep(&p_full[rs.stage], rs.phase, 20);
+#endif
+            ST_TRACE(0, n, 1);
+            ensure(ok_v, &v_full[rv.stage], rv.phase);
+            ensure(ok_o, o_free, (tn - 1) & 1);
+            if (s_valid) {
+              ensure(ok_k, &k_full[rk.stage], rk.phase);
+              ensure(ok_q, &q_full[rq.stage], rq.phase);
+            }
+            ST_TRACE(0, n, 3);
+          }
+          __syncwarp();
           tc_fence_after();
           const uint64_t dv = dv0 + static_cast<uint32_t>(rv.stage) * kStageStep;
           const uint32_t pa = tb + rs.stage * kS;  // P(n): per key half 32 columns of packed bf16 pairs
-          if (lane == 0) ST_TRACE(0, n, 4);
           if (elect_one()) {
+            ST_TRACE(0, n, 4);
 #pragma unroll
             for (int kb = 0; kb < 2; ++kb) {  // key half kb accumulates into its own O (own softmax reference)
 #pragma unroll
@@ -318,16 +367,17 @@ __global__ void __launch_bounds__(kThreads, 1) attn_stream_kernel(const __grid_c
                 umma_bf16_ts(tb + col_o + kb * kHD, pa + kb * 64 + 8 * k, dv + kb * (64 * 128 >> 4) + 128 * k, idesc_o,
                              (j == 0 && k == 0) ? 0u : 1u);
             }
-            ST_TRACE(0, n, 5);
-            umma_commit(&v_free[rv.stage]);
             if (j + 1 == ns) umma_commit(o_full);
+            if (s_valid) s_mmas();
+            ST_TRACE(0, n, 5);
+            umma_commit(&s_full[rs_s.stage]);  // S(n+3) complete; without further slabs it still marks "PV(n) done"
           }
           __syncwarp();
+          if (s_valid) s_advance();
+          rs_s.advance(kSBufs);
           rv.advance(kVStages);
           rs.advance(kSBufs);
           if (lane == 0) ST_TRACE(0, n, 2);
-          if (tile_s < p.total_tiles) issue_s();
-          if (lane == 0) ST_TRACE(0, n, 3);
         }
       }
     }
@@ -340,12 +390,14 @@ __global__ void __launch_bounds__(kThreads, 1) attn_stream_kernel(const __grid_c
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     float2* xchg = reinterpret_cast<float2*>(smem + kOffX);
     uint32_t n = 0, tn = 0;
-    Ring rk, rq, rv, rs;  // K / Q stages to release; V ring position of slab n (its v_free doubles as "PV(n) done"); S buffer
+    Ring rk, rq, rv_rel, rs;  // K / Q stages to release; V stage of slab n - 2; S buffer of slab n
     const float scale = p.scale_log2;
 
     // The scores of slab n+1 are fetched while slab n is still being exponentiated (its buffer is the other one and
     // S runs two slabs ahead), so the barrier probe and the TMEM read latency sit under the MUFU stream.
     uint32_t va[32], vb[32];
+    bool pending = false;  // P of the previous slab written but not yet published
+    Ring rs_pending;
     warp_mbar_wait_sleep(&s_full[0], 0, 20);
     tc_fence_after();
     constexpr uint32_t col_o_base = kSBufs * kS;
@@ -376,10 +428,16 @@ __global__ void __launch_bounds__(kThreads, 1) attn_stream_kernel(const __grid_c
         const uint32_t t_s = t_lane + rs.stage * kS + half * 64;
         const uint32_t t_next = t_lane + rs_next.stage * kS + half * 64;
         float o_factor = 1.0f;  // what O_h (slabs 0..j-1 of the tile) must be multiplied by before PV(n) accumulates
-        const Ring rv_prev = rv;
 
         const bool tracer = quad == 0 && lane == 0;
         if (tracer) ST_TRACE(1 + half, n, 0);
+        // probe S(n+1) now, use the answer after the first chunk: a barrier probe costs ~240 cycles even on success
+        bool next_ready = true;
+#if ST_EARLYPROBE
+        if (has_next && lane == 0) next_ready = mbar_try_wait(&s_full[rs_next.stage], rs_next.phase);
+#else
+        if (lane == 0) next_ready = false;
+#endif
         tmem_ld_wait();  // all 64 scores of slab n are in registers: their columns may be overwritten from here on
         if (tracer) ST_TRACE(1 + half, n, 2);
         if (lead) {  // S(n) is complete: its K stage (and, after the tile's last slab, Q) is free
@@ -388,7 +446,6 @@ __global__ void __launch_bounds__(kThreads, 1) attn_stream_kernel(const __grid_c
         }
         rk.advance(kKStages);
         if (j + 1 == t.n_slabs) rq.advance(kQStages);
-        rv.advance(kVStages);
 
         auto chunk = [&](uint32_t(&v)[32], int c, bool live) {
           uint32_t packed[16];
@@ -409,10 +466,19 @@ __global__ void __launch_bounds__(kThreads, 1) attn_stream_kernel(const __grid_c
               float e0, e1, e2, e3;
               ffma2(e0, e1, __uint_as_float(v[k]), __uint_as_float(v[k + 1]), scale, noff);
               ffma2(e2, e3, __uint_as_float(v[k + 2]), __uint_as_float(v[k + 3]), scale, noff);
+#if ST_ABL == 1  // ablation: no MUFU at all (wrong results; timing only)
+              e0 *= 0.001f; e1 *= 0.001f; e2 *= 0.001f; e3 *= 0.001f;
+#elif ST_ABL == 2  // ablation: half the exponentials
+              e0 = fast_exp2(e0);
+              e1 *= 0.001f;
+              e2 = fast_exp2(e2);
+              e3 *= 0.001f;
+#else
               e0 = fast_exp2(e0);
               e1 = fast_exp2(e1);
               e2 = fast_exp2(e2);
               e3 = fast_exp2(e3);
+#endif
               fadd2(a0, a1, e0, e1);
               fadd2(a2, a3, e2, e3);
               packed[k >> 1] = pack_bf16(e0, e1);
@@ -468,12 +534,20 @@ __global__ void __launch_bounds__(kThreads, 1) attn_stream_kernel(const __grid_c
 #pragma unroll
             for (int k = 0; k < 16; ++k) packed[k] = 0u;
           }
+          if (c == 0 && pending) {  // publish P(n-1) now: its stores were issued a whole chunk ago, so the wait is free
+            tmem_st_wait();
+            tc_fence_before();
+            warp_mbar_arrive(&p_full[rs_pending.stage]);
+            pending = false;
+          }
           tmem_st_32x16(t_s + c * 16, packed);
         };
         chunk(va, 0, live0);
         if (tracer) ST_TRACE(1 + half, n, 3);
         if (has_next) {  // slab n+1's scores, first chunk: va is free
-          warp_mbar_wait_sleep(&s_full[rs_next.stage], rs_next.phase, 20);
+          if (!next_ready) mbar_wait_sleep(&s_full[rs_next.stage], rs_next.phase, 20);  // lane 0 only
+          if (lead && n >= 2) mbar_arrive(&v_free[rv_rel.stage]);  // S(n+1) complete => PV(n-2), issued before it, too
+          __syncwarp();
           tc_fence_after();
           tmem_ld_32x32(t_next, va);
         }
@@ -483,8 +557,9 @@ __global__ void __launch_bounds__(kThreads, 1) attn_stream_kernel(const __grid_c
         if (has_next) tmem_ld_32x32(t_next + 32, vb);
 
         if (j > 0 && __any_sync(0xffffffffu, o_factor != 1.0f)) {  // rare: bring O_h down to the new reference
-          warp_mbar_wait(&v_free[rv_prev.stage == 0 ? kVStages - 1 : rv_prev.stage - 1],
-                         rv_prev.stage == 0 ? rv_prev.phase ^ 1 : rv_prev.phase);  // PV(n-1) has landed in O_h
+          Ring rs_nn = rs_next;
+          rs_nn.advance(kSBufs);
+          warp_mbar_wait(&s_full[rs_nn.stage], rs_nn.phase);  // S(n+2)'s commit follows PV(n-1): it has landed in O_h
           tc_fence_after();
 #pragma unroll 1
           for (int hh = 0; hh < 2; ++hh) {
@@ -496,10 +571,17 @@ __global__ void __launch_bounds__(kThreads, 1) attn_stream_kernel(const __grid_c
             tmem_st_32x32(t_lane + col_o + hh * 32, o);
           }
         }
+#if ST_DEFER
+        // P(n) (and a rescaled O_h) are published after the first chunk of the next slab, when the stores have landed
+        rs_pending = rs;
+        pending = true;
+#else
         tmem_st_wait();  // P(n) (and a rescaled O_h) are in tensor memory
         tc_fence_before();
         warp_mbar_arrive(&p_full[rs.stage]);
+#endif
         rs = rs_next;
+        if (n >= 2) rv_rel.advance(kVStages);
         if (tracer) ST_TRACE(1 + half, n, 5);
       }
 
@@ -507,6 +589,11 @@ __global__ void __launch_bounds__(kThreads, 1) attn_stream_kernel(const __grid_c
       if (tn >= 2) warp_mbar_wait_sleep(&x_free[tn & 1], ((tn >> 1) & 1) ^ 1, 20);
       xchg[((tn & 1) * 2 + half) * kQ + row] = make_float2(ref, sum);
       warp_mbar_arrive(&x_full[tn & 1]);
+    }
+    if (pending) {
+      tmem_st_wait();
+      tc_fence_before();
+      warp_mbar_arrive(&p_full[rs_pending.stage]);
     }
   } else if (warp >= 12) {
     // ---- epilogue: (w0 O0 + w1 O1) / (w0 s0 + w1 s1) -> bf16 -> global; log-sum-exp for the backward
@@ -519,7 +606,14 @@ __global__ void __launch_bounds__(kThreads, 1) attn_stream_kernel(const __grid_c
       const Tile t = decode_tile(p, tile);
       const int q = t.q0 + row;
       const uint32_t par = (tn >> 1) & 1;
-      warp_mbar_wait_sleep(&x_full[tn & 1], par, 200);
+      // the previous tile's TMA store has read the staging tile (per-thread rows would touch 32 cache lines per
+      // store instruction and hold the LSU for ~1 000 cycles per tile, which every mbarrier operation of the CTA
+      // queues behind: tools/attn_stream_trace.py showed all roles stalling at tile boundaries)
+#if ST_EPI_EARLY
+      if (warp == 12 && lane == 0) tma_store_wait_read<0>();
+      named_bar_sync(1, 128);
+#endif
+      warp_mbar_wait_sleep(&x_full[tn & 1], par, 100);
       const float2 ha = xchg[((tn & 1) * 2 + 0) * kQ + row];
       const float2 hb = xchg[((tn & 1) * 2 + 1) * kQ + row];
       warp_mbar_arrive(&x_free[tn & 1]);
@@ -532,11 +626,10 @@ __global__ void __launch_bounds__(kThreads, 1) attn_stream_kernel(const __grid_c
       constexpr uint32_t col_o = kSBufs * kS;
       warp_mbar_wait_sleep(o_full, tn & 1, 40);
       tc_fence_after();
-      // the previous tile's TMA store has read the staging tile (per-thread rows would touch 32 cache lines per
-      // store instruction and hold the LSU for ~1 000 cycles per tile, which every mbarrier operation of the CTA
-      // queues behind: tools/attn_stream_trace.py showed all roles stalling at tile boundaries)
+#if !ST_EPI_EARLY
       if (warp == 12 && lane == 0) tma_store_wait_read<0>();
       named_bar_sync(1, 128);
+#endif
       const uint32_t st_row = smem_u32(smem + kOffOut) + row * 128;
       const int swz = row & 7;
 #pragma unroll 1

@@ -109,7 +109,7 @@ def _attn_ref(qkv, B, T, H, hd, mask):
     return (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B * T, D)
 
 
-@pytest.mark.parametrize("algo", [ops.ATTN_MMA_SYNC, ops.ATTN_TCGEN05, ops.ATTN_FA])
+@pytest.mark.parametrize("algo", [ops.ATTN_MMA_SYNC, ops.ATTN_TCGEN05, ops.ATTN_FA, ops.ATTN_STREAM])
 @pytest.mark.parametrize("B,T,H,W", [(2, 300, 3, 128), (1, 512, 2, 8), (3, 64, 1, 128), (2, 2048, 2, 128),
                                      (2, 130, 2, None), (4, 128, 3, None), (1, 256, 1, None), (2, 1000, 2, 100),
                                      (1, 129, 1, 128)])
@@ -143,6 +143,8 @@ def test_attn_window_kernel_rejects_what_it_cannot_do():
     qkv72 = bf(torch.randn(2 * 128, 3 * 72, device=DEV))
     with pytest.raises(_lib.OsuditError):                                        # head_dim 72 is mma.sync only
         ops.attn_band(qkv72, torch.empty(2 * 128, 72, device=DEV, dtype=torch.bfloat16), 2, 128, 1, 72, algo=ops.ATTN_FA)
+    with pytest.raises(_lib.OsuditError):
+        ops.attn_band(qkv72, torch.empty(2 * 128, 72, device=DEV, dtype=torch.bfloat16), 2, 128, 1, 72, algo=ops.ATTN_STREAM)
 
 
 def _attn_ref_lse(qkv, B, T, H, hd, wl, wr):
@@ -158,29 +160,34 @@ def _attn_ref_lse(qkv, B, T, H, hd, wl, wr):
 
 @pytest.mark.parametrize("B,T,H,wl,wr", [(2, 128, 3, -1, -1), (3, 100, 2, -1, -1), (2, 512, 4, -1, -1), (1, 1, 1, -1, -1),
                                          (1, 640, 2, 300, 10), (5, 128, 7, -1, -1), (1, 1000, 1, 63, 64),
-                                         (2, 2048, 1, 127, 128)])
-def test_attn_streaming_kernel_output_and_log_sum_exp(B, T, H, wl, wr):
-    """csrc/attn_fa.cu (tcgen05, two query tiles in flight, online softmax over 128-key slabs): the training forward
+                                         (2, 2048, 1, 127, 128), (150, 128, 2, -1, -1), (40, 384, 4, 127, 128)])
+@pytest.mark.parametrize("algo", [ops.ATTN_STREAM, ops.ATTN_FA])
+def test_attn_streaming_kernel_output_and_log_sum_exp(B, T, H, wl, wr, algo):
+    """csrc/attn_stream.cu / csrc/attn_fa.cu (tcgen05, online softmax over 128-key slabs): the training forward
     (models.py:164-170 under train.py:249-255) needs the row log-sum-exp next to the output; asymmetric bands, ragged
-    tails, full attention over several slabs, a single token."""
+    tails, full attention over several slabs, a single token, more tiles than SMs (every CTA walks several tiles)."""
     hd = 64
     g = torch.Generator(device=DEV).manual_seed(B * 1000 + T)
     qkv = bf(torch.randn(B * T, 3 * H * hd, device=DEV, generator=g) * 1.5)
     out = torch.full((B * T, H * hd), float("nan"), device=DEV, dtype=torch.bfloat16)
     lse = torch.full((B, H, T), float("nan"), device=DEV)
-    ops.attn_band(qkv, out, B, T, H, hd, wl, wr, None, ops.ATTN_FA, lse=lse)
+    ops.attn_band(qkv, out, B, T, H, hd, wl, wr, None, algo, lse=lse)
     ref, lse_ref = _attn_ref_lse(qkv, B, T, H, hd, wl, wr)
     assert not bool(torch.isnan(out.float()).any())
     assert rel(out.float(), ref) < 6e-3
     assert float((lse - lse_ref).abs().max()) < 1e-3  # log2 domain
-    # and AUTO with lse picks the same kernel: identical bits
-    out2, lse2 = torch.empty_like(out), torch.empty_like(lse)
-    ops.attn_band(qkv, out2, B, T, H, hd, wl, wr, None, ops.ATTN_AUTO, lse=lse2)
-    assert torch.equal(out, out2) and torch.equal(lse, lse2)
+    if algo == ops.ATTN_STREAM:  # AUTO picks this kernel, with and without lse: identical bits
+        out2, lse2 = torch.empty_like(out), torch.empty_like(lse)
+        ops.attn_band(qkv, out2, B, T, H, hd, wl, wr, None, ops.ATTN_AUTO, lse=lse2)
+        assert torch.equal(out, out2) and torch.equal(lse, lse2)
+        out3 = torch.empty_like(out)
+        ops.attn_band(qkv, out3, B, T, H, hd, wl, wr, None, ops.ATTN_AUTO)
+        assert torch.equal(out, out3)
 
 
+@pytest.mark.parametrize("algo", [ops.ATTN_STREAM, ops.ATTN_FA])
 @pytest.mark.parametrize("T,wl,wr,ramp", [(1024, -1, -1, 12.0), (1024, 255, 256, 40.0), (512, -1, -1, 0.0)])
-def test_attn_streaming_kernel_rescales_the_accumulator(T, wl, wr, ramp):
+def test_attn_streaming_kernel_rescales_the_accumulator(T, wl, wr, ramp, algo):
     """Rows whose scores keep growing along the keys (by far more than the 2^24 the lazy power-of-two reference
     tolerates) force the rare path: P of the current slab, the running sums and O in TMEM are rescaled by an exact
     power of two.  ramp = 0: scores of wide range without a trend."""
@@ -196,7 +203,7 @@ def test_attn_streaming_kernel_rescales_the_accumulator(T, wl, wr, ramp):
         qkv = bf(torch.randn(T, 3 * H * hd, device=DEV, generator=g) * 6.0)
     out = torch.full((T, H * hd), float("nan"), device=DEV, dtype=torch.bfloat16)
     lse = torch.empty(B, H, T, device=DEV)
-    ops.attn_band(qkv, out, B, T, H, hd, wl, wr, None, ops.ATTN_FA, lse=lse)
+    ops.attn_band(qkv, out, B, T, H, hd, wl, wr, None, algo, lse=lse)
     ref, lse_ref = _attn_ref_lse(qkv, B, T, H, hd, wl, wr)
     assert bool(torch.isfinite(out.float()).all())
     assert rel(out.float(), ref) < 6e-3

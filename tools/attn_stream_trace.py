@@ -30,9 +30,9 @@ lib.osudit_debug_stream_trace.argtypes = [ctypes.c_void_p]
 assert lib.osudit_debug_stream_trace(buf.ctypes.data) == 0
 tr = buf.reshape(3, 48, 6)
 t0 = tr[tr > 0].min()
-mn = ["top", "p_full ok", "PV issued", "S(n+2) issued", "v_full ok", "PV mmas out"]
+mn = ["top", "p_full ok", "done", "operands ok", "elected", "mmas out"]
 sn = ["top", "s_full ok", "ld landed", "chunk0", "chunk1", "p_full arrived"]
 for n in range(0, 24):
-    print(f"slab {12 + n}  mma: " + " ".join(f"{mn[e]}={tr[0, n, e] - t0}" for e in (0, 1, 4, 5, 2, 3)))
+    print(f"slab {12 + n}  mma: " + " ".join(f"{mn[e]}={tr[0, n, e] - t0}" for e in (0, 1, 3, 4, 5, 2)))
     for h in range(2):
         print(f"      softmax half {h}: " + " ".join(f"{sn[e]}={tr[1 + h, n, e] - t0}" for e in range(6)))
