@@ -461,7 +461,7 @@ def kernel_roofline(model, diffusion, zd, od, cd, yd, mask_d, device):
                            "achieved": round(lb / (lms / 1e3) / 1e9, 1), "peak": hbm_peak, "unit": "GB/s",
                            "frac": round(lb / (lms / 1e3) / 1e9 / hbm_peak, 4), "launches_timed": ln_n,
                            "share_of_step": round(lms / step_ms, 3)},
-            "attention_kernel": {"kernel": "attn_tc::attn_window_kernel" if SIZES[MODEL][0] // SIZES[MODEL][2] == 64
+            "attention_kernel": {"kernel": "attn_st::attn_stream_kernel (tcgen05, P in TMEM)" if SIZES[MODEL][0] // SIZES[MODEL][2] == 64
                                  else "attn_band_kernel<72> (mma.sync)", "achieved": round(af / (ams / 1e3) / 1e12, 1),
                                  "unit": "TFLOP/s (banded algorithmic flops)", "share_of_step": round(ams / step_ms, 3)}}
 

@@ -54,6 +54,21 @@ namespace attn_st {
 #ifndef ST_EARLYPROBE
 #define ST_EARLYPROBE 1
 #endif
+// Sleep between probes of a barrier that is not complete yet (ns).  A polling loop costs issue slots and entries of
+// the memory-instruction queue on the scheduler it shares with two softmax warps; the producers and the epilogue
+// warps have a whole tile of slack, a softmax warp that has to wait for scores is AHEAD of its row partner.
+#ifndef ST_SLEEP_PROD
+#define ST_SLEEP_PROD 100
+#endif
+#ifndef ST_SLEEP_SOFT
+#define ST_SLEEP_SOFT 20
+#endif
+#ifndef ST_SLEEP_EPI
+#define ST_SLEEP_EPI 100
+#endif
+#ifndef ST_SKEW
+#define ST_SKEW 0
+#endif
 #ifndef ST_PWAIT
 #define ST_PWAIT 0
 #endif
@@ -84,6 +99,7 @@ struct Params {
   float* lse;           // [B, H, T] or nullptr
   int B, T, H, D;
   int q_tiles, total_tiles;
+  int step_q, step_r;   // gridDim.x / q_tiles, gridDim.x % q_tiles
   int w_left, w_right;  // allowed iff -w_left <= key - query <= w_right
   float scale_log2;
 };
@@ -124,19 +140,36 @@ struct Tile {
   int b, h, q0, slab_lo, n_slabs;
 };
 
-__device__ __forceinline__ Tile decode_tile(const Params& p, int tile) {
-  Tile t;
-  const int qt = tile % p.q_tiles;
-  const int bh = tile / p.q_tiles;
-  t.h = bh % p.H;
-  t.b = bh / p.H;
-  t.q0 = qt * kQ;
-  const int kmin = max(t.q0 - p.w_left, 0);
-  const int kmax = min(t.q0 + kQ - 1 + p.w_right, p.T - 1);
-  t.slab_lo = kmin / kS;
-  t.n_slabs = kmax / kS - t.slab_lo + 1;
-  return t;
-}
+// The tiles of a CTA: blockIdx.x, + gridDim.x, ...  One division at the start, then (query tile, batch * head) move
+// by the precomputed quotient / remainder of gridDim.x by q_tiles: the per-tile decode sat on the MMA warp's path.
+struct Walk {
+  int tile, qt, bh;
+  __device__ __forceinline__ void init(const Params& p, int t0) {
+    tile = t0;
+    qt = t0 % p.q_tiles;
+    bh = t0 / p.q_tiles;
+  }
+  __device__ __forceinline__ void next(const Params& p, int G) {
+    tile += G;
+    qt += p.step_r;
+    bh += p.step_q;
+    if (qt >= p.q_tiles) {
+      qt -= p.q_tiles;
+      ++bh;
+    }
+  }
+  __device__ __forceinline__ Tile get(const Params& p, bool need_bh) const {
+    Tile t;
+    t.h = need_bh ? bh % p.H : 0;
+    t.b = need_bh ? bh / p.H : 0;
+    t.q0 = qt * kQ;
+    const int kmin = max(t.q0 - p.w_left, 0);
+    const int kmax = min(t.q0 + kQ - 1 + p.w_right, p.T - 1);
+    t.slab_lo = kmin / kS;
+    t.n_slabs = kmax / kS - t.slab_lo + 1;
+    return t;
+  }
+};
 
 // A position in a ring of `stages` buffers; `phase` is the parity of the number of completed laps.
 struct Ring {
@@ -226,14 +259,15 @@ __global__ void __launch_bounds__(kThreads, 1) attn_stream_kernel(const __grid_c
     // ------------------------------------------------------------------ TMA producer: Q tiles and K slabs
     if (lane == 0) {
       Ring rq, rk;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += G) {
-        const Tile t = decode_tile(p, tile);
-        mbar_wait_sleep(&q_free[rq.stage], rq.phase ^ 1, 100);
+      Walk w;
+      for (w.init(p, blockIdx.x); w.tile < p.total_tiles; w.next(p, G)) {
+        const Tile t = w.get(p, true);
+        mbar_wait_sleep(&q_free[rq.stage], rq.phase ^ 1, ST_SLEEP_PROD);
         mbar_expect_tx(&q_full[rq.stage], kTile);
         tma_load_3d(ring_q + rq.stage * kTile, &p.tma_qkv, &q_full[rq.stage], t.h * kHD, t.q0, t.b);
         rq.advance(kQStages);
         for (int j = 0; j < t.n_slabs; ++j) {
-          mbar_wait_sleep(&k_free[rk.stage], rk.phase ^ 1, 100);
+          mbar_wait_sleep(&k_free[rk.stage], rk.phase ^ 1, ST_SLEEP_PROD);
           mbar_expect_tx(&k_full[rk.stage], kTile);
           tma_load_3d(ring_k + rk.stage * kTile, &p.tma_qkv, &k_full[rk.stage], p.D + t.h * kHD,
                       (t.slab_lo + j) * kS, t.b);
@@ -245,10 +279,11 @@ __global__ void __launch_bounds__(kThreads, 1) attn_stream_kernel(const __grid_c
     // ------------------------------------------------------------------ TMA producer: V slabs
     if (lane == 0) {
       Ring rv;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += G) {
-        const Tile t = decode_tile(p, tile);
+      Walk w;
+      for (w.init(p, blockIdx.x); w.tile < p.total_tiles; w.next(p, G)) {
+        const Tile t = w.get(p, true);
         for (int j = 0; j < t.n_slabs; ++j) {
-          mbar_wait_sleep(&v_free[rv.stage], rv.phase ^ 1, 100);
+          mbar_wait_sleep(&v_free[rv.stage], rv.phase ^ 1, ST_SLEEP_PROD);
           mbar_expect_tx(&v_full[rv.stage], kTile);
           tma_load_3d(ring_v + rv.stage * kTile, &p.tma_qkv, &v_full[rv.stage], 2 * p.D + t.h * kHD,
                       (t.slab_lo + j) * kS, t.b);
@@ -288,7 +323,9 @@ __global__ void __launch_bounds__(kThreads, 1) attn_stream_kernel(const __grid_c
         if (!ok) mbar_wait_sleep(bar, parity, 20);  // lane 0 only
       };
       // S cursor: the slab whose scores are issued next (three ahead of the PV cursor)
-      int tile_s = blockIdx.x, j_s = 0, ns_s = decode_tile(p, tile_s).n_slabs;
+      Walk ws;
+      ws.init(p, blockIdx.x);
+      int j_s = 0, ns_s = ws.get(p, false).n_slabs;
       Ring rq, rk, rs_s;
       auto s_mmas = [&]() {  // elected lane
         const uint64_t dq = dq0 + static_cast<uint32_t>(rq.stage) * kStageStep;
@@ -301,13 +338,13 @@ __global__ void __launch_bounds__(kThreads, 1) attn_stream_kernel(const __grid_c
         rk.advance(kKStages);
         if (++j_s == ns_s) {
           j_s = 0;
-          tile_s += G;
+          ws.next(p, G);
           rq.advance(kQStages);
-          if (tile_s < p.total_tiles) ns_s = decode_tile(p, tile_s).n_slabs;
+          ns_s = ws.get(p, false).n_slabs;
         }
       };
       for (int i = 0; i < kSBufs; ++i) {
-        if (tile_s < p.total_tiles) {
+        if (ws.tile < p.total_tiles) {
           if (lane == 0) {
             if (j_s == 0) mbar_wait_sleep(&q_full[rq.stage], rq.phase, 20);
             mbar_wait_sleep(&k_full[rk.stage], rk.phase, 20);
@@ -325,11 +362,12 @@ __global__ void __launch_bounds__(kThreads, 1) attn_stream_kernel(const __grid_c
       }
       uint32_t n = 0, tn = 0;
       Ring rv, rs;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += G, ++tn) {
-        const int ns = decode_tile(p, tile).n_slabs;
+      Walk w;
+      for (w.init(p, blockIdx.x); w.tile < p.total_tiles; w.next(p, G), ++tn) {
+        const int ns = w.get(p, false).n_slabs;
         constexpr uint32_t col_o = kSBufs * kS;
         for (int j = 0; j < ns; ++j, ++n) {
-          const bool s_valid = tile_s < p.total_tiles;
+          const bool s_valid = ws.tile < p.total_tiles;
           const bool ok_v = probe(&v_full[rv.stage], rv.phase);
           const bool ok_k = !s_valid || probe(&k_full[rk.stage], rk.phase);
           const bool ok_q = !(s_valid && j_s == 0) || probe(&q_full[rq.stage], rq.phase);
@@ -395,6 +433,11 @@ __global__ void __launch_bounds__(kThreads, 1) attn_stream_kernel(const __grid_c
 
     // The scores of slab n+1 are fetched while slab n is still being exponentiated (its buffer is the other one and
     // S runs two slabs ahead), so the barrier probe and the TMEM read latency sit under the MUFU stream.
+#if ST_SKEW > 0
+    // The two threads of a row would otherwise run in lockstep (same barriers, same work): both in their MUFU phase,
+    // then both in the scalar part of the slab, with the XU pipe idle.  Half 1 starts late and stays late.
+    if (half == 1) __nanosleep(ST_SKEW);
+#endif
     uint32_t va[32], vb[32];
     bool pending = false;  // P of the previous slab written but not yet published
     Ring rs_pending;
@@ -404,8 +447,10 @@ __global__ void __launch_bounds__(kThreads, 1) attn_stream_kernel(const __grid_c
     tmem_ld_32x32(t_lane + half * 64, va);
     tmem_ld_32x32(t_lane + half * 64 + 32, vb);
 
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += G, ++tn) {
-      const Tile t = decode_tile(p, tile);
+    Walk w;
+    for (w.init(p, blockIdx.x); w.tile < p.total_tiles; w.next(p, G), ++tn) {
+      const Tile t = w.get(p, false);
+      const int tile = w.tile;
       const int q = t.q0 + row;
       const uint32_t col_o = col_o_base + half * kHD;
       float ref = -INFINITY;  // this half's running reference (integer-valued, log2 domain)
@@ -486,6 +531,13 @@ __global__ void __launch_bounds__(kThreads, 1) attn_stream_kernel(const __grid_c
             }
             csum = (a0 + a1) + (a2 + a3);
           };
+#if ST_ABL == 3  // ablation: no softmax arithmetic at all (wrong results; the floor of the pipeline around it)
+          if (live) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) packed[k] = v[2 * k] & 0x3f803f80u;
+            sum += 1.0f;
+          } else
+#endif
           if (live) {  // warp-uniform
             const int base = c * 32;
             if (!(base >= c_lo && base + 31 <= c_hi)) {  // boundary chunk: masked scores become -inf
@@ -545,7 +597,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_stream_kernel(const __grid_c
         chunk(va, 0, live0);
         if (tracer) ST_TRACE(1 + half, n, 3);
         if (has_next) {  // slab n+1's scores, first chunk: va is free
-          if (!next_ready) mbar_wait_sleep(&s_full[rs_next.stage], rs_next.phase, 20);  // lane 0 only
+          if (!next_ready) mbar_wait_sleep(&s_full[rs_next.stage], rs_next.phase, ST_SLEEP_SOFT);  // lane 0 only
           if (lead && n >= 2) mbar_arrive(&v_free[rv_rel.stage]);  // S(n+1) complete => PV(n-2), issued before it, too
           __syncwarp();
           tc_fence_after();
@@ -602,8 +654,9 @@ __global__ void __launch_bounds__(kThreads, 1) attn_stream_kernel(const __grid_c
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     const float2* xchg = reinterpret_cast<const float2*>(smem + kOffX);
     uint32_t tn = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += G, ++tn) {
-      const Tile t = decode_tile(p, tile);
+    Walk w;
+    for (w.init(p, blockIdx.x); w.tile < p.total_tiles; w.next(p, G), ++tn) {
+      const Tile t = w.get(p, true);
       const int q = t.q0 + row;
       const uint32_t par = (tn >> 1) & 1;
       // the previous tile's TMA store has read the staging tile (per-thread rows would touch 32 cache lines per
@@ -613,7 +666,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_stream_kernel(const __grid_c
       if (warp == 12 && lane == 0) tma_store_wait_read<0>();
       named_bar_sync(1, 128);
 #endif
-      warp_mbar_wait_sleep(&x_full[tn & 1], par, 100);
+      warp_mbar_wait_sleep(&x_full[tn & 1], par, ST_SLEEP_EPI);
       const float2 ha = xchg[((tn & 1) * 2 + 0) * kQ + row];
       const float2 hb = xchg[((tn & 1) * 2 + 1) * kQ + row];
       warp_mbar_arrive(&x_free[tn & 1]);
@@ -702,6 +755,8 @@ int attn_stream_launch(const void* qkv, void* out, int B, int T, int H, int w_le
     configured = true;
   }
   const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  p.step_q = grid / p.q_tiles;
+  p.step_r = grid % p.q_tiles;
   attn_stream_kernel<<<grid, kThreads, kSmemBytes, stream>>>(p);
   OSUDIT_CHECK_LAUNCH();
   return 0;

@@ -245,35 +245,50 @@ gemm2_kernel(const __grid_constant__ Params p) {
     }
   } else if (warp == 1) {
     // -------------------------------------------------------------- MMA issuer (leader only)
-    if (leader && lane == 0) {
+    // The whole warp runs the loop converged and one elected lane issues.  Inside an `if (lane == 0)` region the
+    // compiler cannot prove the operands of tcgen05.mma / tcgen05.commit warp-uniform (they must sit in uniform
+    // registers), and wraps every one of them in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop of ~16 instructions:
+    // with four MMAs of 128 tensor cycles per k-block the issue then runs about as long as the execution.
+    if (leader) {
       // kind::f16: D fp32, A/B bf16 K-major, N = BN, M = 256 (pair)
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(BN >> 3) << 17) |
                                  (static_cast<uint32_t>((2 * BM) >> 4) << 24);
+      const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);  // provably warp-uniform
+      const uint32_t sbase = smem_u32(smem);
+      const uint64_t da0 = desc_sw128(sbase), db0 = desc_sw128(sbase + kBytesA);
+      constexpr uint32_t kStageStep = kStageBytes >> 4;  // descriptor address field counts 16-byte units (< 256 KB: no carry)
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       int it = 0;
       for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++it) {
-        GEMM_TRACE(0, it, 0);
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        if (lane == 0) {
+          GEMM_TRACE(0, it, 0);
+          mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+          GEMM_TRACE(0, it, 1);
+        }
+        __syncwarp();
         tc_fence_after();
-        GEMM_TRACE(0, it, 1);
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+        const uint32_t d_tmem = tb + static_cast<uint32_t>(acc * BN);
         for (int kb = 0; kb < p.kblocks; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+          if (lane == 0) mbar_wait(&full_bar[stage], phase);
+          __syncwarp();
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * kStageBytes);
-          const uint64_t da = desc_sw128(sa);
-          const uint64_t db = desc_sw128(sa + kBytesA);
+          const uint64_t da = da0 + static_cast<uint32_t>(stage) * kStageStep;
+          const uint64_t db = db0 + static_cast<uint32_t>(stage) * kStageStep;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            umma_bf16_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit_pair(&empty_bar[stage]);
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit_pair(&empty_bar[stage]);
+          }
+          __syncwarp();
           if (++stage == kSt) { stage = 0; phase ^= 1; }
         }
-        umma_commit_pair(&tmem_full[acc]);
-        GEMM_TRACE(0, it, 2);
+        if (elect_one()) umma_commit_pair(&tmem_full[acc]);
+        __syncwarp();
+        if (lane == 0) GEMM_TRACE(0, it, 2);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
