@@ -166,73 +166,55 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
     }
   } else if (warp == 1) {
     // -------------------------------------------------------------------- MMA issuer
-    // The whole warp runs the loop converged and one elected lane issues (see gemm_2cta.cu: inside an
-    // `if (lane == 0)` region every tcgen05.mma is wrapped in an ELECT / R2UR / BRA.U.ANY loop, ~130 cycles each
-    // for the 32 small MMAs of a problem).
-    {
+    if (lane == 0) {
       constexpr uint32_t id_s = idesc(128, false, false);   // S, dP: both operands K-major
       constexpr uint32_t id_t = idesc(kHD, true, true);     // dV, dK: A = P^T / dS^T and B both MN-major
       constexpr uint32_t id_q = idesc(kHD, false, true);    // dQ: A = dS K-major, B = K MN-major
-      const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);  // provably warp-uniform
-      const uint32_t sbase = smem_u32(smem);
-      const uint32_t sP = sbase + kOffP, sDS = sbase + kOffDS;
+      const uint32_t sP = smem_u32(smem + kOffP), sDS = smem_u32(smem + kOffDS);
       auto issue_sdp = [&](int i) {
         const int st = i & 1;
-        const uint32_t base = sbase + st * kStage;
-        if (lane == 0) mbar_wait(&in_full[st], (i >> 1) & 1);
-        __syncwarp();
+        const uint32_t base = smem_u32(smem + st * kStage);
+        mbar_wait(&in_full[st], (i >> 1) & 1);
         tc_fence_after();
         const uint64_t dq = desc_sw128(base), dk = desc_sw128(base + kTile);
         const uint64_t dv = desc_sw128(base + 2 * kTile), ddo = desc_sw128(base + 3 * kTile);
-        if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kHD / 16; ++k) umma_bf16(tb + kColS, dq + 2 * k, dk + 2 * k, id_s, k != 0);
+        for (int k = 0; k < kHD / 16; ++k) umma_bf16(tmem_base + kColS, dq + 2 * k, dk + 2 * k, id_s, k != 0);
 #pragma unroll
-          for (int k = 0; k < kHD / 16; ++k) umma_bf16(tb + kColDP, ddo + 2 * k, dv + 2 * k, id_s, k != 0);
-          umma_commit(sdp_full);
-        }
-        __syncwarp();
+        for (int k = 0; k < kHD / 16; ++k) umma_bf16(tmem_base + kColDP, ddo + 2 * k, dv + 2 * k, id_s, k != 0);
+        umma_commit(sdp_full);
       };
       if (n_my > 0) issue_sdp(0);
       for (int i = 0; i < n_my; ++i) {
-        if (lane == 0) {
-          BWD_TRACE(0, i, 0);
-          mbar_wait_sleep(p_full, i & 1, 32);  // S / dP of problem i read, P / dS in shared memory
-          BWD_TRACE(0, i, 1);
-        }
-        __syncwarp();
+        BWD_TRACE(0, i, 0);
+        mbar_wait_sleep(p_full, i & 1, 32);  // S / dP of problem i read, P / dS in shared memory
+        BWD_TRACE(0, i, 1);
         if (i + 1 < n_my) issue_sdp(i + 1);
-        if (lane == 0) {
-          BWD_TRACE(0, i, 2);
-          mbar_wait_sleep(g_free, (i & 1) ^ 1, 32);  // the epilogue has read problem i-1's gradients out of TMEM
-          BWD_TRACE(0, i, 3);
-        }
-        __syncwarp();
+        BWD_TRACE(0, i, 2);
+        mbar_wait_sleep(g_free, (i & 1) ^ 1, 32);  // the epilogue has read problem i-1's gradients out of TMEM
+        BWD_TRACE(0, i, 3);
         tc_fence_after();
-        const uint32_t base = sbase + (i & 1) * kStage;
+        const uint32_t base = smem_u32(smem + (i & 1) * kStage);
         // MN-major A: keys 0-63 / 64-127 are the two column blocks of the [query][key] tile, 16 KB apart;
         // one K = 16 step = 16 query rows = 2 KB
         const uint64_t a_p = desc_sw128(sP, kTile), a_ds = desc_sw128(sDS, kTile);
         const uint64_t b_q = desc_sw128(base), b_do = desc_sw128(base + 3 * kTile);
-        if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kT / 16; ++k)  // dV[key][d] = sum_q P[q][key] dO[q][d]
-            umma_bf16(tb + kColDV, a_p + 128 * k, b_do + 128 * k, id_t, k != 0);
+        for (int k = 0; k < kT / 16; ++k)  // dV[key][d] = sum_q P[q][key] dO[q][d]
+          umma_bf16(tmem_base + kColDV, a_p + 128 * k, b_do + 128 * k, id_t, k != 0);
 #pragma unroll
-          for (int k = 0; k < kT / 16; ++k)  // dK[key][d] = sum_q dS[q][key] Q[q][d]
-            umma_bf16(tb + kColDK, a_ds + 128 * k, b_q + 128 * k, id_t, k != 0);
+        for (int k = 0; k < kT / 16; ++k)  // dK[key][d] = sum_q dS[q][key] Q[q][d]
+          umma_bf16(tmem_base + kColDK, a_ds + 128 * k, b_q + 128 * k, id_t, k != 0);
 #pragma unroll
-          for (int kb = 0; kb < 2; ++kb) {   // dQ[q][d] = sum_key dS[q][key] K[key][d]
-            const uint64_t a = desc_sw128(sDS + kb * kTile);
-            const uint64_t bk = desc_sw128(base + kTile + kb * (64 * 128));
+        for (int kb = 0; kb < 2; ++kb) {   // dQ[q][d] = sum_key dS[q][key] K[key][d]
+          const uint64_t a = desc_sw128(sDS + kb * kTile);
+          const uint64_t bk = desc_sw128(base + kTile + kb * (64 * 128));
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16(tb + kColDQ, a + 2 * k, bk + 128 * k, id_q, (kb | k) != 0);
-          }
-          umma_commit(g_full);
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base + kColDQ, a + 2 * k, bk + 128 * k, id_q, (kb | k) != 0);
         }
-        __syncwarp();
-        if (lane == 0) BWD_TRACE(0, i, 4);
+        umma_commit(g_full);
+        BWD_TRACE(0, i, 4);
       }
     }
   } else if (warp >= 4 && warp < 12) {

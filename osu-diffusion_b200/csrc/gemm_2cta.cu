@@ -248,7 +248,10 @@ gemm2_kernel(const __grid_constant__ Params p) {
     // The whole warp runs the loop converged and one elected lane issues.  Inside an `if (lane == 0)` region the
     // compiler cannot prove the operands of tcgen05.mma / tcgen05.commit warp-uniform (they must sit in uniform
     // registers), and wraps every one of them in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop of ~16 instructions:
-    // with four MMAs of 128 tensor cycles per k-block the issue then runs about as long as the execution.
+    // with four MMAs of 128 tensor cycles per k-block the issue then runs about as long as the execution.  Measured
+    // (tools/gemm_bench.py): fc1+GELU 1362 -> 1436, QKV 1410 -> 1435 TFLOP/s, out-proj and fc2 unchanged.  The same
+    // change made the 1-CTA kernel (64-cycle MMAs, a __syncwarp per k-block on its critical path) and the attention
+    // backward slightly slower (training step 25.56 -> 25.84 ms), so those keep the single-lane loop.
     if (leader) {
       // kind::f16: D fp32, A/B bf16 K-major, N = BN, M = 256 (pair)
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(BN >> 3) << 17) |

@@ -203,22 +203,17 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
     }
   } else if (warp == 1) {
     // -------------------------------------------------------------- MMA issuer
-    // The whole warp runs the loop converged and one elected lane issues (see gemm_2cta.cu: inside an
-    // `if (lane == 0)` region every tcgen05.mma is wrapped in an ELECT / R2UR / BRA.U.ANY loop).
-    {
+    if (lane == 0) {
       // MN-major operands (EPI_WGRAD): bits 15/16 of the instruction descriptor
       constexpr uint32_t idesc = umma_idesc<BN>() | (kWgrad ? (3u << 15) : 0u);
-      const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);  // provably warp-uniform
-      const uint32_t sbase = smem_u32(smem);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int work = blockIdx.x; work < total_tiles; work += gridDim.x) {
-        if (lane == 0) mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-        __syncwarp();
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tb + static_cast<uint32_t>(acc * BN);
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
         int n_kb = total_kblocks;
         if (kWgrad) {
           const int kb0 = split_of(work) * p.kb_per_split;
@@ -228,36 +223,31 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
           n_kb = min(g_lo + p.kb_per_split, total_kblocks) - g_lo;
         }
         for (int kb = 0; kb < n_kb; ++kb) {
-          if (lane == 0) mbar_wait(&full_bar[stage], phase);
-          __syncwarp();
+          mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = sbase + stage * C::kStageBytes;
-          if (elect_one()) {
-            if (kWgrad) {
-              // MN-major SWIZZLE_128B: 64-element atoms along M/N are 8 KB apart (LBO), 8-row K groups
-              // 1 KB apart (SBO); one K=16 step = 16 rows = 2 KB
-              const uint64_t lbo = static_cast<uint64_t>((8192 >> 4) - 1) << 16;  // umma_desc sets 1
-              const uint64_t da = umma_desc_sw128(sa) + lbo;
-              const uint64_t db = umma_desc_sw128(sa + kStageBytesA) + lbo;
+          const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
+          if (kWgrad) {
+            // MN-major SWIZZLE_128B: 64-element atoms along M/N are 8 KB apart (LBO), 8-row K groups
+            // 1 KB apart (SBO); one K=16 step = 16 rows = 2 KB
+            const uint64_t lbo = static_cast<uint64_t>((8192 >> 4) - 1) << 16;  // umma_desc sets 1
+            const uint64_t da = umma_desc_sw128(sa) + lbo;
+            const uint64_t db = umma_desc_sw128(sa + kStageBytesA) + lbo;
 #pragma unroll
-              for (int k = 0; k < BK / UMMA_K; ++k)
-                umma_bf16(d_tmem, da + 128 * k, db + 128 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-            } else {
-              const uint64_t da = umma_desc_sw128(sa);
-              const uint64_t db = umma_desc_sw128(sa + kStageBytesA);
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              umma_bf16(d_tmem, da + 128 * k, db + 128 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          } else {
+            const uint64_t da = umma_desc_sw128(sa);
+            const uint64_t db = umma_desc_sw128(sa + kStageBytesA);
 #pragma unroll
-              for (int k = 0; k < BK / UMMA_K; ++k) {
-                // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in 16 B units
-                umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-              }
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in 16 B units
+              umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
             }
-            umma_commit(&empty_bar[stage]);
           }
-          __syncwarp();
+          umma_commit(&empty_bar[stage]);
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
-        if (elect_one()) umma_commit(&tmem_full[acc]);
-        __syncwarp();
+        umma_commit(&tmem_full[acc]);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }

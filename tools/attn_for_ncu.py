@@ -1,4 +1,4 @@
-"""The attention kernels at the shapes the model runs them, for ncu (profiles/README.md): the streaming forward at
+"""The attention kernels at the shapes the model runs them, for ncu (profiles/README.md): the streaming forward (attn_stream.cu) at
 BASELINE config 3 (256 x 128, with log-sum-exp) and config 5 per GPU (128 x 512), the window kernel at config 2,
 and the tcgen05 backward at config 3.  Not a benchmark."""
 import os, sys
@@ -14,7 +14,7 @@ for B, T, H, wl, wr, bwd in [(256, 128, 12, -1, -1, True), (128, 512, 16, -1, -1
     out = torch.empty(B * T, D, device=dev, dtype=torch.bfloat16)
     lse = torch.empty(B, H, T, device=dev)
     for _ in range(3):
-        ops.attn_band(qkv, out, B, T, H, hd, wl, wr, None, ops.ATTN_FA, lse=lse)
+        ops.attn_band(qkv, out, B, T, H, hd, wl, wr, None, ops.ATTN_STREAM, lse=lse if bwd else None)
         if wl >= 0:
             ops.attn_band(qkv, out, B, T, H, hd, wl, wr, None, ops.ATTN_TCGEN05)
         if bwd:
