@@ -110,6 +110,20 @@ int osudit_repack_weights(const void* segments, int nseg, int total_tiles, void*
  * backward == 0: out = gelu_tanh(pre);  backward == 1: out = dy * gelu_tanh'(pre).  bf16, n % 8 == 0. */
 int osudit_gelu(const void* pre, const void* dy, void* out, int64_t n, int backward, void* stream);
 
+/* The gated residual update of a DiT block done by the GEMM that produces the branch (inference):
+ *   x[M, N] (fp32) += gate[row / rows_per_batch, :] * (A[M, K] B[N, K]^T + bias)
+ * Replaces `x = x + gate_msa.unsqueeze(1) * self.attn(...)` and `x = x + gate_mlp.unsqueeze(1) * self.mlp(...)`
+ * (models.py:164-174) for the out-projection / fc2 Linear: the epilogue multiplies by the gate and adds into the
+ * residual stream with an fp32 TMA reduce-add, so the branch is never written and the LayerNorm kernel that follows
+ * only reads x (6 D instead of 12 D bytes per token).  gate: fp32, row b at gate + b * gate_ld (elements).
+ * CTA-pair kernel only: osudit_gemm_gated_residual_applicable(M, N, rows_per_batch) != 0 says whether the shape is
+ * taken (N % 256 == 0 or N % 192 == 0, rows_per_batch % 128 == 0 and dividing M, >= 37 output tiles); otherwise
+ * use osudit_gemm_bf16 + osudit_ln_modulate with a branch. */
+int osudit_gemm_gated_residual_applicable(int64_t M, int64_t N, int64_t rows_per_batch);
+int osudit_gemm_gated_residual(const void* a, int64_t lda, const void* b, int64_t ldb, int64_t K, int64_t M, int64_t N,
+                               const float* bias, const float* gate, int64_t gate_ld, int64_t rows_per_batch, float* x,
+                               int64_t ldx, void* stream);
+
 /* Single-segment bf16 GEMM (as osudit_gemm_bf16) whose epilogue also touches a second bf16 [M, N] tensor `aux`:
  *   OSUDIT_EPI_BF16_GELU_SAVE: out = gelu_tanh(A B^T + bias), aux = gelu_tanh'(A B^T + bias): all the backward needs
  *                              from the fc1 pre-activation                     (training forward, models.py:112-119)

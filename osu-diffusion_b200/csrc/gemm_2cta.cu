@@ -55,12 +55,13 @@ struct Cfg {
   static constexpr int kBiasBytes = kEpiGroups * 2 * BN * 4;  // bias slice of the current / next tile, per epilogue group
   static constexpr int kSmemBytes = kStages * kStageBytes + 2 * kEpiGroups * kStagingBytes + 1024 + kBiasBytes;
 };
-// EPI_BF16_DGELU gives one operand stage to the two TMA-staged chunks of its auxiliary operand
-__host__ __device__ constexpr int stages_for(int epi) { return epi == 4 ? kStages - 1 : kStages; }
+// EPI_BF16_DGELU gives one operand stage to the two TMA-staged chunks of its auxiliary operand; EPI_RESID (5) to a
+// second pair of fp32 staging boxes (its chunks are 32 KB, double-buffered like the 16 KB bf16 chunks of the others)
+__host__ __device__ constexpr int stages_for(int epi) { return (epi == 4 || epi == 5) ? kStages - 1 : kStages; }
 template <int BN>
 constexpr int smem_bytes_for(int epi) {
-  return stages_for(epi) * Cfg<BN>::kStageBytes + (epi == 4 ? 2 * kStagingBytes : 0) + 2 * kEpiGroups * kStagingBytes + 1024 +
-         Cfg<BN>::kBiasBytes;
+  return stages_for(epi) * Cfg<BN>::kStageBytes + ((epi == 4 || epi == 5) ? 2 * kStagingBytes : 0) +
+         2 * kEpiGroups * kStagingBytes + 1024 + Cfg<BN>::kBiasBytes;
 }
 
 struct Params {
@@ -69,6 +70,9 @@ struct Params {
   const float* bias;
   const __nv_bfloat16* aux;  // EPI_BF16_DGELU: the saved GELU derivative, read straight from global memory
   int64_t ld_aux;
+  const float* gate;         // EPI_RESID: gate[b, n] at gate + b * gate_ld + n, b = row / rows_per_batch
+  int64_t gate_ld;
+  int rows_per_batch, batches;
 };
 
 // EPI_BF16_GELU_SAVE (training forward of fc1): out = gelu(acc + bias) and aux = gelu'(acc + bias) — the only
@@ -77,7 +81,12 @@ struct Params {
 // EPI_BF16_DGELU (training backward through the GELU): out = acc * aux, the data gradient of fc2 multiplied by the
 // saved derivative in the epilogue (one multiply per element; ncu showed the tensor pipe at 43 % when the
 // derivative was recomputed here), so du is never materialised.
-enum : int { EPI_BF16 = 1, EPI_BF16_GELU = 2, EPI_BF16_GELU_SAVE = 3, EPI_BF16_DGELU = 4 };
+// EPI_RESID (inference): the gated residual update of the block, x += gate * (acc + bias) (models.py:164-174), done
+// here as an fp32 TMA reduce-add into the residual stream instead of writing a bf16 branch that the next
+// LayerNorm kernel reads back and folds in: that kernel is HBM-bound (12 D bytes per token: x in, branch in, x out,
+// h out) and drops to 6 D (x in, h out); the 6 D move into this GEMM, which has HBM headroom.  The branch is no
+// longer rounded to bf16 on the way.
+enum : int { EPI_BF16 = 1, EPI_BF16_GELU = 2, EPI_BF16_GELU_SAVE = 3, EPI_BF16_DGELU = 4, EPI_RESID = 5 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -184,7 +193,7 @@ gemm2_kernel(const __grid_constant__ Params p) {
   constexpr bool kAuxTma = EPI == EPI_BF16_DGELU;  // the saved GELU derivative is staged by TMA, two chunks ahead
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* aux_smem = smem + kSt * kStageBytes;  // [2][128 rows][64 cols] bf16, 128-byte swizzled (DGELU only)
-  uint8_t* staging = aux_smem + (kAuxTma ? 2 * kStagingBytes : 0);
+  uint8_t* staging = aux_smem + ((kAuxTma || EPI == EPI_RESID) ? 2 * kStagingBytes : 0);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + 2 * kEpiGroups * kStagingBytes);
   uint64_t* empty_bar = full_bar + kSt;
   uint64_t* tmem_full = empty_bar + kSt;
@@ -329,8 +338,14 @@ gemm2_kernel(const __grid_constant__ Params p) {
       // the thread's own row cost 32 cache lines per load instruction and held this GEMM at 43 % tensor-pipe activity.
       // this tile's 256 bias values go through shared memory (one global load per thread per tile, issued before
       // the wait for the accumulator) instead of 8 dependent __ldg per thread per chunk on the critical path
-      float* s_bias = s_bias_all + (grp * 2 + (it & 1)) * BN;
+      // (EPI_RESID: bias in the first buffer, this tile's gate slice in the second; the per-chunk barriers order the
+      // previous tile's reads before these writes)
+      float* s_bias = s_bias_all + (grp * 2 + (EPI == EPI_RESID ? 0 : (it & 1))) * BN;
       if (ep_tid < BN) s_bias[ep_tid] = p.bias != nullptr ? __ldg(p.bias + n0 + ep_tid) : 0.f;
+      if (EPI == EPI_RESID && ep_tid < BN) {
+        const int b = min(m0 / p.rows_per_batch, p.batches - 1);  // the CTA's 128 rows lie in one batch row
+        s_bias[BN + ep_tid] = __ldg(p.gate + static_cast<int64_t>(b) * p.gate_ld + n0 + ep_tid);
+      }
       if (ep_tid == 0) GEMM_TRACE(1, it, 0);
       warp_mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
@@ -367,6 +382,38 @@ gemm2_kernel(const __grid_constant__ Params p) {
           v[i + 1] = __uint_as_float(r[i + 1]) + b.y;
           v[i + 2] = __uint_as_float(r[i + 2]) + b.z;
           v[i + 3] = __uint_as_float(r[i + 3]) + b.w;
+        }
+        if (EPI == EPI_RESID) {
+          const float* s_gate = s_bias + BN + c * 64 + half * 32;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 g = *reinterpret_cast<const float4*>(s_gate + i);
+            v[i + 0] *= g.x;
+            v[i + 1] *= g.y;
+            v[i + 2] *= g.z;
+            v[i + 3] *= g.w;
+          }
+          // two [128 rows][32 columns] fp32 boxes (one per column half): the group's staging pair and the pair in
+          // the auxiliary area alternate per chunk, so one chunk's reduce-add may still be reading while the next is
+          // written (kEpiGroups == 1 is the shipped configuration; with two groups both would share the second pair)
+          static_assert(EPI != EPI_RESID || kEpiGroups == 1, "EPI_RESID: one epilogue group");
+          uint8_t* pair = (chunk_ctr & 1) ? aux_smem : my_staging;
+          ++chunk_ctr;
+          if (ep_tid == 0) tma_store_wait_read<1>();
+          named_bar_sync(1 + grp, 256);
+          uint8_t* my_row = pair + half * kStagingBytes + row * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(my_row + ((j ^ (row & 7)) << 4)) =
+                make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          fence_proxy_async_smem();
+          named_bar_sync(1 + grp, 256);
+          if (ep_tid == 0) {
+            tma_reduce_add_2d(&p.tma_out, pair, ncol0, m0);
+            tma_reduce_add_2d(&p.tma_out, pair + kStagingBytes, ncol0 + 32, m0);
+            tma_store_commit();
+          }
+          continue;
         }
         if (EPI == EPI_BF16_DGELU) {
 #pragma unroll
@@ -473,6 +520,42 @@ extern "C" int osudit_debug_gemm_trace(long long* host_out) {
 }
 #endif
 
+bool gemm_2cta_resid_applicable(int64_t M, int64_t N, int64_t rows_per_batch) {
+  if (!(N % 256 == 0 || N % 192 == 0) || rows_per_batch <= 0 || rows_per_batch % g2::BM != 0 || M % rows_per_batch != 0)
+    return false;
+  const int64_t tiles = ((M + 255) / 256) * (N % 256 == 0 ? N / 256 : N / 192);
+  return M >= 256 && tiles >= 37;
+}
+
+// x[M, N] (fp32) += gate[row / rows_per_batch, :] * (a[M, K] b[N, K]^T + bias)
+int gemm_2cta_resid_launch(const void* a, int64_t lda, const void* b, int64_t ldb, int64_t K, int64_t M, int64_t N,
+                           const float* bias, const float* gate, int64_t gate_ld, int64_t rows_per_batch, float* x,
+                           int64_t ldx, cudaStream_t stream) {
+  using namespace g2;
+  const int BN = N % 256 == 0 ? 256 : 192;
+  Params p;
+  p.kblocks = static_cast<int>((K + BK - 1) / BK);
+  p.M = static_cast<int>(M);
+  p.N = static_cast<int>(N);
+  p.m_tiles = static_cast<int>((M + 2 * BM - 1) / (2 * BM));
+  p.n_tiles = static_cast<int>(N / BN);
+  p.bias = bias;
+  p.aux = nullptr;
+  p.ld_aux = 0;
+  p.gate = gate;
+  p.gate_ld = gate_ld;
+  p.rows_per_batch = static_cast<int>(rows_per_batch);
+  p.batches = static_cast<int>(M / rows_per_batch);
+  int rc = make_tensor_map_2d(&p.tma_a, a, K, M, lda * 2, BK, BM, false);
+  if (rc) return rc;
+  rc = make_tensor_map_2d(&p.tma_b, b, K, N, ldb * 2, BK, BN / 2, false);
+  if (rc) return rc;
+  rc = make_tensor_map_2d(&p.tma_out, x, N, M, ldx * 4, 32, BM, true);  // fp32 boxes of 32 columns = 128 bytes
+  if (rc) return rc;
+  p.tma_aux = p.tma_out;
+  return BN == 256 ? launch2<EPI_RESID, 256>(p, stream) : launch2<EPI_RESID, 192>(p, stream);
+}
+
 bool gemm_2cta_applicable(int nseg, int64_t M, int64_t N, int epilogue) {
   if (!(nseg == 1 && epilogue >= g2::EPI_BF16 && epilogue <= g2::EPI_BF16_DGELU && (N % 256 == 0 || N % 192 == 0)))
     return false;
@@ -502,6 +585,10 @@ int gemm_2cta_launch(const void* a, int64_t lda, const void* b, int64_t ldb, int
   if (rc) return rc;
   p.aux = static_cast<const __nv_bfloat16*>(aux);
   p.ld_aux = ld_aux;
+  p.gate = nullptr;
+  p.gate_ld = 0;
+  p.rows_per_batch = 1;
+  p.batches = 1;
   p.tma_aux = p.tma_out;
   if (epilogue == EPI_BF16_GELU_SAVE || epilogue == EPI_BF16_DGELU) {
     if (aux == nullptr || (ld_aux % 8) != 0) return set_error(-1, "gemm: aux must be given with ld_aux % 8 == 0");

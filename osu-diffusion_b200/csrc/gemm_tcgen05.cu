@@ -563,6 +563,30 @@ extern "C" int osudit_gemm_bf16_aux(const void* a, int64_t lda, const void* b, i
   return gelu_aux_launch(aux, out, M * N, 1, static_cast<cudaStream_t>(stream));
 }
 
+namespace osudit {
+bool gemm_2cta_resid_applicable(int64_t M, int64_t N, int64_t rows_per_batch);
+int gemm_2cta_resid_launch(const void* a, int64_t lda, const void* b, int64_t ldb, int64_t K, int64_t M, int64_t N,
+                           const float* bias, const float* gate, int64_t gate_ld, int64_t rows_per_batch, float* x,
+                           int64_t ldx, cudaStream_t stream);
+}
+
+extern "C" int osudit_gemm_gated_residual_applicable(int64_t M, int64_t N, int64_t rows_per_batch) {
+  return gemm_2cta_resid_applicable(M, N, rows_per_batch) ? 1 : 0;
+}
+
+extern "C" int osudit_gemm_gated_residual(const void* a, int64_t lda, const void* b, int64_t ldb, int64_t K, int64_t M,
+                                          int64_t N, const float* bias, const float* gate, int64_t gate_ld,
+                                          int64_t rows_per_batch, float* x, int64_t ldx, void* stream) {
+  if (M <= 0 || N <= 0 || K <= 0 || (K % 8) || (N % 8) || (lda % 8) || (ldb % 8) || (ldx % 4))
+    return set_error(-1, "gemm_gated_residual: bad shape");
+  if (a == nullptr || b == nullptr || gate == nullptr || x == nullptr) return set_error(-1, "gemm_gated_residual: null operand");
+  if (!gemm_2cta_resid_applicable(M, N, rows_per_batch))
+    return set_error(-1, "gemm_gated_residual: needs N % 256 == 0 or N % 192 == 0, rows_per_batch % 128 == 0 dividing M, "
+                         "and at least 37 output tiles (ask osudit_gemm_gated_residual_applicable first)");
+  return gemm_2cta_resid_launch(a, lda, b, ldb, K, M, N, bias, gate, gate_ld, rows_per_batch, x, ldx,
+                                static_cast<cudaStream_t>(stream));
+}
+
 extern "C" int osudit_gemm_bf16_splitk(int nseg, const void* const* a, const int64_t* lda,
                                        const void* const* b, const int64_t* ldb, const int64_t* k,
                                        int64_t M, int64_t N, const float* bias, int kb_per_split,

@@ -50,6 +50,8 @@ SIGNATURES = {
     "osudit_cfg_combine": [_P, _I, _I, _F, _P, _P],
     "osudit_q_sample": [_P, _P, _P, _P, _P, _I, _L, _P, _P],
     "osudit_gemm_bf16_aux": [_P, _L, _P, _L, _L, _L, _L, _P, _I, _P, _L, _P, _L, _P],
+    "osudit_gemm_gated_residual": [_P, _L, _P, _L, _L, _L, _L, _P, _P, _L, _L, _P, _L, _P],
+    "osudit_gemm_gated_residual_applicable": [_L, _L, _L],
     "osudit_beatmap_features": [_P, _I, _I, _I, _P, _P, _P, _P, _P, _P],
     "osudit_opt_chunk_elems": [],
     "osudit_adamw_ema_step": [_P, _P, _I, _F, _F, _F, _F, _F, _F, _P, _P, _P, _P],

@@ -9,6 +9,7 @@ allocate nothing and reuse the same TMA descriptors.
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 
@@ -35,6 +36,7 @@ class MaskSpec:
 
 _mask_cache: dict = {}  # key -> (MaskSpec, the mask tensor): the entry keeps the tensor (and so its address) alive
 _MASK_CACHE_ENTRIES = 16
+_RESID_EPILOGUE = os.environ.get("OSUDIT_GEMM_RESID", "1") != "0"
 
 
 def classify_mask(attn_mask, T: int) -> MaskSpec:
@@ -284,18 +286,29 @@ class DiTEngine:
             mod = self.conditioning(ws, t, y, w)
 
         xres, h, qkv, att, yb, u = ws["x"], ws["h"], ws["qkv"], ws["att"], ws["y"], ws["u"]
+        # The gated residual updates (models.py:164-174) run in the epilogue of the out-projection / fc2 GEMMs when the
+        # CTA-pair kernel takes the shape (an fp32 TMA reduce-add into the residual stream): the LayerNorm kernels,
+        # HBM-bound, then only read x (6 D bytes per token instead of 12 D).  OSUDIT_GEMM_RESID=0 keeps the bf16 branch.
+        fused = _RESID_EPILOGUE and ops.gemm_gated_residual_applicable(B * T, D, T)
         for i, bw in enumerate(w.blocks):
             base = 6 * D * i
-            if i == 0:
+            if i == 0 or fused:
                 ops.ln_modulate(xres, None, mod, 0, base, base + D, T, h)
             else:  # fold the previous block's gated MLP residual into this LayerNorm pass
                 ops.ln_modulate(xres, yb, mod, base - D, base, base + D, T, h)
             ops.gemm([h], [bw["qkv_w"]], bw["qkv_b"], ops.EPI_BF16, qkv)
             ops.attn_band(qkv, att, B, T, H, D // H, spec.w_left, spec.w_right, spec.generic)
-            ops.gemm([att], [bw["out_w"]], bw["out_b"], ops.EPI_BF16, yb)
-            ops.ln_modulate(xres, yb, mod, base + 2 * D, base + 3 * D, base + 4 * D, T, h)
+            if fused:
+                ops.gemm_gated_residual(att, bw["out_w"], bw["out_b"], mod, base + 2 * D, T, xres)
+                ops.ln_modulate(xres, None, mod, 0, base + 3 * D, base + 4 * D, T, h)
+            else:
+                ops.gemm([att], [bw["out_w"]], bw["out_b"], ops.EPI_BF16, yb)
+                ops.ln_modulate(xres, yb, mod, base + 2 * D, base + 3 * D, base + 4 * D, T, h)
             ops.gemm([h], [bw["fc1_w"]], bw["fc1_b"], ops.EPI_BF16_GELU, u)
-            ops.gemm([u], [bw["fc2_w"]], bw["fc2_b"], ops.EPI_BF16, yb)
+            if fused:
+                ops.gemm_gated_residual(u, bw["fc2_w"], bw["fc2_b"], mod, base + 5 * D, T, xres)
+            else:
+                ops.gemm([u], [bw["fc2_w"]], bw["fc2_b"], ops.EPI_BF16, yb)
         fbase = 6 * D * self.depth
-        ops.final_layer(xres, yb, mod, fbase - D, fbase, fbase + D, T, w.final_w, w.final_b, ws["out"])
+        ops.final_layer(xres, None if fused else yb, mod, fbase - D, fbase, fbase + D, T, w.final_w, w.final_b, ws["out"])
         return ws["out"]

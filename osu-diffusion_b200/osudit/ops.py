@@ -74,6 +74,27 @@ def gemm_aux(a, w, bias, epilogue: int, out, aux):
     return out
 
 
+def gemm_gated_residual_applicable(M: int, N: int, rows_per_batch: int) -> bool:
+    return bool(_lib.load().osudit_gemm_gated_residual_applicable(M, N, rows_per_batch))
+
+
+def gemm_gated_residual(a, w, bias, mod, gate_col: int, rows_per_batch: int, x):
+    """x fp32 [M, N] += mod[row // rows_per_batch, gate_col : gate_col + N] * (a @ w.T + bias): the block's gated
+    residual update (models.py:164-174) in the epilogue of the GEMM that produces the branch."""
+    M, N = x.shape
+    if a.shape[0] != M or w.shape[0] != N or a.shape[1] != w.shape[1]:
+        raise _lib.OsuditError(f"gemm_gated_residual: shape mismatch {tuple(a.shape)} x {tuple(w.shape)} -> {tuple(x.shape)}")
+    _chk(mod, torch.float32, "gemm_gated_residual.mod")
+    lib = _lib.load()
+    _lib.check(lib.osudit_gemm_gated_residual(_chk(a, torch.bfloat16, "gemm_gated_residual.a"), a.stride(0),
+                                              _chk(w, torch.bfloat16, "gemm_gated_residual.w"), w.stride(0), a.shape[1],
+                                              M, N, _chk(bias, torch.float32, "gemm_gated_residual.bias") if bias is not None else None,
+                                              _off(mod, gate_col), mod.stride(0), rows_per_batch,
+                                              _chk(x, torch.float32, "gemm_gated_residual.x"), x.stride(0), _stream()),
+               "osudit_gemm_gated_residual")
+    return x
+
+
 ATTN_AUTO, ATTN_MMA_SYNC, ATTN_TCGEN05, ATTN_FA, ATTN_STREAM = 0, 1, 2, 3, 4
 
 

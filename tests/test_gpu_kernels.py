@@ -333,3 +333,32 @@ def test_diffusion_step_matches_oracle(cfg):
                        1.5, True, 2, sample, x0, x0_in=x0_cb)
     torch.testing.assert_close(sample.cpu(), ref2["sample"], rtol=2e-6, atol=2e-6)
     torch.testing.assert_close(x0.cpu(), ref2["pred_xstart"], rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("M,N,K,T", [(128 * 80, 768, 768, 2048), (128 * 80, 768, 3072, 128), (256 * 37, 1152, 1152, 256),
+                                     (128 * 75, 384, 1536, 128 * 25)])
+def test_gemm_gated_residual(M, N, K, T):
+    """models.py:164-174: x = x + gate.unsqueeze(1) * Linear(branch input), the Linear's GEMM adding gate * (acc + bias)
+    into the fp32 residual stream itself (TMA reduce-add).  Rows per batch row = T; the last 256-row tile may be half
+    empty (M = 75 x 128)."""
+    g = torch.Generator(device=DEV).manual_seed(M + N + K)
+    a = bf(torch.randn(M, K, device=DEV, generator=g))
+    w = bf(torch.randn(N, K, device=DEV, generator=g) / math.sqrt(K))
+    bias = torch.randn(N, device=DEV, generator=g)
+    Bn = M // T
+    mod = torch.randn(Bn, 3 * N + 8, device=DEV, generator=g)
+    x0 = torch.randn(M, N, device=DEV, generator=g)
+    assert ops.gemm_gated_residual_applicable(M, N, T)
+    x = x0.clone()
+    ops.gemm_gated_residual(a, w, bias, mod, N + 8, T, x)
+    gate = mod[:, N + 8:2 * N + 8].repeat_interleave(T, 0)
+    ref = x0.double() + gate.double() * (a.double() @ w.double().t() + bias.double())
+    assert bool(torch.isfinite(x).all())
+    assert rel(x, ref) < 1e-5                      # fp32 accumulate and fp32 add: no bf16 rounding of the branch
+    assert float((x.double() - ref).abs().max()) < 2e-4
+    # shapes the CTA-pair kernel does not take are refused, not silently mishandled
+    assert not ops.gemm_gated_residual_applicable(M, N, T + 1)
+    assert not ops.gemm_gated_residual_applicable(256, N, 128)
+    from osudit import _lib
+    with pytest.raises(_lib.OsuditError):
+        ops.gemm_gated_residual(a[:256], w, bias, mod, 0, 128, x[:256])
