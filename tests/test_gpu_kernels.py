@@ -241,6 +241,25 @@ def test_ln_modulate(D, branch):
     assert float((h.float() - bf(h_ref).float()).abs().max()) < 4e-2
 
 
+@pytest.mark.parametrize("D,B,T", [(768, 5, 1001), (1152, 3, 2048), (384, 37, 128), (1024, 2, 2051)])
+def test_ln_modulate_read_only_streaming_kernel(D, B, T):
+    """models.py:12-13,160-163 without a pending residual update (the GEMM epilogues add the branches): from 4096 rows
+    up the persistent bulk-copy kernel runs — groups of 8 rows, ragged last group, batch rows that change inside a
+    group; x must stay untouched."""
+    rows = B * T
+    x = torch.randn(rows, D, device=DEV) * 2 + 0.5
+    x0 = x.clone()
+    mod = torch.randn(B, 6 * D, device=DEV) * 0.3
+    ln = torch.nn.functional.layer_norm(x, (D,), eps=1e-6)
+    h_ref = ln * (1 + mod[:, D:2 * D].repeat_interleave(T, 0)) + mod[:, :D].repeat_interleave(T, 0)
+    h = torch.full((rows, D), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.ln_modulate(x, None, mod, 0, 0, D, T, h)
+    assert torch.equal(x, x0)
+    assert bool(torch.isfinite(h.float()).all())
+    assert rel(h.float(), h_ref) < 3e-3
+    assert float((h.float() - bf(h_ref).float()).abs().max()) < 4e-2
+
+
 @pytest.mark.parametrize("D", [384, 768, 1152])
 def test_final_layer(D):
     B, T = 2, 77
