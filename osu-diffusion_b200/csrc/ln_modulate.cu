@@ -11,7 +11,6 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
-#include <stdlib.h>
 
 #include "common.h"
 #include "ptx.cuh"
@@ -108,99 +107,6 @@ ln_modulate_kernel(float* __restrict__ x, const __nv_bfloat16* __restrict__ y,
   }
 }
 
-// Read-only variant (no pending residual update: the GEMM epilogues add the branches, gemm_2cta.cu EPI_RESID):
-// 4 D bytes in, 2 D out per token.  With one warp per row and plain loads it reached 0.78 of the copy bandwidth
-// (0.71 inside the sampling step).  Here a persistent CTA per SM streams groups of 8 consecutive rows: one 1-D bulk
-// copy (cp.async.bulk, 8 * D * 4 contiguous bytes) per group into a ring of four shared-memory buffers, three groups in
-// flight, each warp normalises one row out of shared memory, the bf16 rows are staged and leave as one bulk store.
-constexpr int kLnGroup = 8;      // rows per group = warps per CTA
-constexpr int kLnInBufs = 4;
-constexpr int kLnOutBufs = 2;
-
-__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void bulk_store_1d(void* gdst, const void* smem_src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-               ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes)
-               : "memory");
-}
-
-template <int NV>
-__global__ void __launch_bounds__(kLnGroup * 32, 1)
-ln_modulate_stream_kernel(const float* __restrict__ x, const float* __restrict__ shift, const float* __restrict__ scale,
-                          int64_t mod_ld, int64_t rows, int T, __nv_bfloat16* __restrict__ h) {
-  constexpr int D = NV * 128;
-  constexpr int kInBytes = kLnGroup * D * 4, kOutBytes = kLnGroup * D * 2;
-  extern __shared__ __align__(128) uint8_t ln_smem[];
-  uint8_t* in_buf = ln_smem;
-  uint8_t* out_buf = ln_smem + kLnInBufs * kInBytes;
-  uint64_t* full = reinterpret_cast<uint64_t*>(out_buf + kLnOutBufs * kOutBytes);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t groups = (rows + kLnGroup - 1) / kLnGroup;
-  const int64_t G = gridDim.x;
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < kLnInBufs; ++i) mbar_init(&full[i], 1);
-    fence_mbar_init();
-  }
-  __syncthreads();
-  auto issue = [&](int64_t it) {  // thread 0: load the it-th group of this CTA
-    const int64_t g = blockIdx.x + it * G;
-    if (g >= groups) return;
-    const int64_t row0 = g * kLnGroup;
-    const uint32_t bytes = static_cast<uint32_t>(min(static_cast<int64_t>(kLnGroup), rows - row0) * D * 4);
-    const int b = static_cast<int>(it % kLnInBufs);
-    mbar_expect_tx(&full[b], bytes);
-    bulk_load_1d(in_buf + b * kInBytes, x + row0 * D, bytes, &full[b]);
-  };
-  if (threadIdx.x == 0)
-    for (int it = 0; it < kLnInBufs - 1; ++it) issue(it);
-  int64_t it = 0;
-  for (int64_t g = blockIdx.x; g < groups; g += G, ++it) {
-    const int b = static_cast<int>(it % kLnInBufs);
-    const int ob = static_cast<int>(it % kLnOutBufs);
-    mbar_wait(&full[b], static_cast<uint32_t>((it / kLnInBufs) & 1));
-    const int64_t row = g * kLnGroup + warp;
-    const bool valid = row < rows;
-    float4 v[NV];
-    const float* src = reinterpret_cast<const float*>(in_buf + b * kInBytes) + warp * D;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) v[i] = valid ? *reinterpret_cast<const float4*>(src + (lane + 32 * i) * 4) : make_float4(0, 0, 0, 0);
-    // the staging buffer written two groups ago must have been read by its bulk store
-    if (threadIdx.x == 0) tma_store_wait_read<kLnOutBufs - 1>();
-    __syncthreads();  // every warp has its row in registers: the input buffer may be refilled; staging is free
-    if (threadIdx.x == 0) issue(it + kLnInBufs - 1);
-    if (valid) {
-      const int64_t bb = row / T;
-      float mean, rstd;
-      row_stats<NV>(v, mean, rstd);
-      const float* sh = shift + bb * mod_ld;
-      const float* sc = scale + bb * mod_ld;
-      uint8_t* dst = out_buf + ob * kOutBytes + warp * D * 2;
-#pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        const int c = (lane + 32 * i) * 4;
-        const float4 s4 = __ldg(reinterpret_cast<const float4*>(sc + c));
-        const float4 t4 = __ldg(reinterpret_cast<const float4*>(sh + c));
-        uint2 o;
-        o.x = pack_bf16(fmaf((v[i].x - mean) * rstd, 1.0f + s4.x, t4.x), fmaf((v[i].y - mean) * rstd, 1.0f + s4.y, t4.y));
-        o.y = pack_bf16(fmaf((v[i].z - mean) * rstd, 1.0f + s4.z, t4.z), fmaf((v[i].w - mean) * rstd, 1.0f + s4.w, t4.w));
-        *reinterpret_cast<uint2*>(dst + c * 2) = o;
-      }
-    }
-    fence_proxy_async_smem();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      const int64_t row0 = g * kLnGroup;
-      bulk_store_1d(h + row0 * D, out_buf + ob * kOutBytes, static_cast<uint32_t>(min(static_cast<int64_t>(kLnGroup), rows - row0) * D * 2));
-      tma_store_commit();
-    }
-  }
-  if (threadIdx.x == 0) tma_store_wait<0>();
-}
-
 // FinalLayer: (pending residual update) -> LN -> modulate -> Linear D -> 4, written channel-major
 // (B, 4, T) like DiT.forward's output (models.py:323-324).  All fp32 (SURVEY F16 keeps the final
 // projection out of bf16).
@@ -270,27 +176,6 @@ struct LnLauncher {
   static int run(float* x, const __nv_bfloat16* y, const float* gate, const float* shift,
                  const float* scale, int64_t mod_ld, int64_t rows, int T, __nv_bfloat16* h,
                  float* x_out, cudaStream_t st) {
-    static const bool stream_ok = [] {  // OSUDIT_LN_STREAM=0: the one-warp-per-row kernel for the read-only case too
-      const char* e = getenv("OSUDIT_LN_STREAM");
-      return !(e && e[0] == '0');
-    }();
-    if (!HB && stream_ok && rows >= 4096) {
-      constexpr int D = NV * 128;
-      constexpr int smem = kLnInBufs * kLnGroup * D * 4 + kLnOutBufs * kLnGroup * D * 2 + kLnInBufs * 8;
-      if (smem <= 227 * 1024) {
-        static bool configured = false;
-        if (!configured) {
-          cudaError_t e = cudaFuncSetAttribute(ln_modulate_stream_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-          if (e != cudaSuccess) return set_error(-5, cudaGetErrorString(e));
-          configured = true;
-        }
-        const int64_t groups = (rows + kLnGroup - 1) / kLnGroup;
-        const unsigned grid = static_cast<unsigned>(groups < num_sms() ? groups : num_sms());
-        ln_modulate_stream_kernel<NV><<<grid, kLnGroup * 32, smem, st>>>(x, shift, scale, mod_ld, rows, T, h);
-        OSUDIT_CHECK_LAUNCH();
-        return 0;
-      }
-    }
     const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
     ln_modulate_kernel<NV, HB><<<grid, 256, 0, st>>>(x, y, gate, shift, scale, mod_ld, rows, T, h, x_out);
     OSUDIT_CHECK_LAUNCH();

@@ -242,10 +242,9 @@ def test_ln_modulate(D, branch):
 
 
 @pytest.mark.parametrize("D,B,T", [(768, 5, 1001), (1152, 3, 2048), (384, 37, 128), (1024, 2, 2051)])
-def test_ln_modulate_read_only_streaming_kernel(D, B, T):
-    """models.py:12-13,160-163 without a pending residual update (the GEMM epilogues add the branches): from 4096 rows
-    up the persistent bulk-copy kernel runs — groups of 8 rows, ragged last group, batch rows that change inside a
-    group; x must stay untouched."""
+def test_ln_modulate_read_only_large(D, B, T):
+    """models.py:12-13,160-163 without a pending residual update (the GEMM epilogues add the branches) at sizes of
+    thousands of rows: ragged row counts, batch rows that change inside a CTA's group of rows; x must stay untouched."""
     rows = B * T
     x = torch.randn(rows, D, device=DEV) * 2 + 0.5
     x0 = x.clone()
