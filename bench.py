@@ -408,7 +408,7 @@ def kernel_roofline(model, diffusion, zd, od, cd, yd, mask_d, device):
         return 2.0 * out.shape[0] * out.shape[1] * sum(a.shape[1] for a in a_segs), tuple(out.shape) + (a_segs[0].shape[1],)
 
     def resid_work(a, w, bias, mod, gate_col, rows_per_batch, x):  # out-projection / fc2 with the residual epilogue
-        return 2.0 * x.shape[0] * x.shape[1] * a.shape[1], tuple(x.shape) + (a.shape[1],)
+        return 2.0 * x.shape[0] * x.shape[1] * a.shape[1], tuple(x.shape) + (a.shape[1], "resid")
 
     def ln_work(x, branch, mod, g, sh, sc, T, h):
         return x.numel() * (12.0 if branch is not None else 6.0), None
@@ -441,10 +441,18 @@ def kernel_roofline(model, diffusion, zd, od, cd, yd, mask_d, device):
     big = lambda tag: tag is not None and tag[0] >= 65536 and tag[2] >= 768  # noqa: E731  (block GEMMs)
     fl, ms, n = agg(rec["gemm"], big)
     by_shape = {}
+    resid = [0.0, 0.0, 0.0]  # flops, ms, algorithmic bytes of the launches that also carry the residual update
+    plain = [0.0, 0.0]
     for e0, e1, (w, tag) in rec["gemm"]:
         if big(tag):
-            d = by_shape.setdefault("x".join(map(str, tag)), [0.0, 0.0])
-            d[0] += w; d[1] += e0.elapsed_time(e1)
+            d = by_shape.setdefault("x".join(map(str, tag[:3])), [0.0, 0.0])
+            t_ms = e0.elapsed_time(e1)
+            d[0] += w; d[1] += t_ms
+            if len(tag) > 3:  # A and W read in bf16, the fp32 residual stream read and written
+                resid[0] += w; resid[1] += t_ms
+                resid[2] += 2.0 * (tag[0] * tag[2] + tag[1] * tag[2]) + 8.0 * tag[0] * tag[1]
+            else:
+                plain[0] += w; plain[1] += t_ms
     lb, lms, ln_n = agg(rec["ln"])
     af, ams, an = agg(rec["attn"])
     step_ms = sum(e0.elapsed_time(e1) for k in rec for e0, e1, _ in rec[k])
@@ -452,7 +460,7 @@ def kernel_roofline(model, diffusion, zd, od, cd, yd, mask_d, device):
     traffic, traffic_src = ncu_gemm_traffic()
     # algorithmic bytes of one launch: A read + W read + out written, bf16 (mean over the timed block GEMMs)
     shapes = [tag for _, _, (w, tag) in rec["gemm"] if big(tag)]
-    algo_gb = sum(2.0 * (m * k + nn * k + m * nn) for m, nn, k in shapes) / max(len(shapes), 1) / 1e9
+    algo_gb = sum(2.0 * (t[0] * t[2] + t[1] * t[2]) + (8.0 if len(t) > 3 else 2.0) * t[0] * t[1] for t in shapes) / max(len(shapes), 1) / 1e9
     return {"bound": "tensor", "kernel": "g2::gemm2_kernel (cta_group::2 tcgen05 GEMM: QKV, fc1+GELU, and out-proj / fc2 "
             "with the gated-residual fp32 reduce-add epilogue)",
             "achieved": round(ach, 1), "peak": tf_peak, "unit": "TFLOP/s", "frac": round(ach / tf_peak, 4),
@@ -460,6 +468,13 @@ def kernel_roofline(model, diffusion, zd, od, cd, yd, mask_d, device):
             f"algorithmic {round(algo_gb, 2)}", "peak_source": src,
             "launches_timed": n,
             "avg_launch_ms": round(ms / max(n, 1), 4), "share_of_step": round(ms / step_ms, 3),
+            "by_epilogue": {
+                "bf16 / GELU (QKV, fc1)": {"achieved": round(plain[0] / max(plain[1], 1e-9) / 1e9, 1), "unit": "TFLOP/s",
+                                            "frac": round(plain[0] / max(plain[1], 1e-9) / 1e9 / tf_peak, 4)},
+                "gated residual (out-proj, fc2): x += gate*(acc+bias) by fp32 TMA reduce-add, 6 D bytes per token moved here "
+                "from the LayerNorm kernel": {"achieved": round(resid[0] / max(resid[1], 1e-9) / 1e9, 1), "unit": "TFLOP/s",
+                                              "hbm_GBs": round(resid[2] / max(resid[1], 1e-9) / 1e6, 1),
+                                              "hbm_frac": round(resid[2] / max(resid[1], 1e-9) / 1e6 / hbm_peak, 4)}},
             "per_shape_tflops": {k: round(v[0] / (v[1] / 1e3) / 1e12, 1) for k, v in by_shape.items()},
             "hbm_kernel": {"kernel": "ln_modulate_kernel", "bound": "hbm",
                            "achieved": round(lb / (lms / 1e3) / 1e9, 1), "peak": hbm_peak, "unit": "GB/s",

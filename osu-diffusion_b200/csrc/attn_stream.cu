@@ -66,6 +66,9 @@ namespace attn_st {
 #ifndef ST_SLEEP_EPI
 #define ST_SLEEP_EPI 100
 #endif
+#ifndef ST_MMA_LANE0
+#define ST_MMA_LANE0 0
+#endif
 #ifndef ST_SKEW
 #define ST_SKEW 0
 #endif
@@ -301,10 +304,10 @@ __global__ void __launch_bounds__(kThreads, 1) attn_stream_kernel(const __grid_c
     // The WHOLE warp runs this loop converged and one elected lane issues: every operand of tcgen05.mma must sit in
     // a uniform register, and inside an `if (lane == 0)` region the compiler cannot prove that, so it wraps each MMA
     // in an ELECT / R2UR / BRA.U.ANY loop.
-    {
+    if (!ST_MMA_LANE0 || lane == 0) {
       constexpr uint32_t idesc_s = idesc(kS, false);
       constexpr uint32_t idesc_o = idesc(kHD, true);
-      const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);  // provably warp-uniform
+      const uint32_t tb = ST_MMA_LANE0 ? tmem_base : __shfl_sync(0xffffffffu, tmem_base, 0);  // provably warp-uniform
       const uint32_t sbase = smem_u32(smem);
       // descriptors of stage 0 of each ring; stage s adds s * (kTile >> 4) to the 14-bit address field (the whole
       // dynamic shared memory lies below 256 KB, so the field cannot carry)
@@ -349,13 +352,13 @@ __global__ void __launch_bounds__(kThreads, 1) attn_stream_kernel(const __grid_c
             if (j_s == 0) mbar_wait_sleep(&q_full[rq.stage], rq.phase, 20);
             mbar_wait_sleep(&k_full[rk.stage], rk.phase, 20);
           }
-          __syncwarp();
+          if (!ST_MMA_LANE0) __syncwarp();
           tc_fence_after();
-          if (elect_one()) {
+          if ((ST_MMA_LANE0 || elect_one())) {
             s_mmas();
             umma_commit(&s_full[rs_s.stage]);
           }
-          __syncwarp();
+          if (!ST_MMA_LANE0) __syncwarp();
           s_advance();
           rs_s.advance(kSBufs);
         }
@@ -392,11 +395,11 @@ __global__ void __launch_bounds__(kThreads, 1) attn_stream_kernel(const __grid_c
             }
             ST_TRACE(0, n, 3);
           }
-          __syncwarp();
+          if (!ST_MMA_LANE0) __syncwarp();
           tc_fence_after();
           const uint64_t dv = dv0 + static_cast<uint32_t>(rv.stage) * kStageStep;
           const uint32_t pa = tb + rs.stage * kS;  // P(n): per key half 32 columns of packed bf16 pairs
-          if (elect_one()) {
+          if ((ST_MMA_LANE0 || elect_one())) {
             ST_TRACE(0, n, 4);
 #pragma unroll
             for (int kb = 0; kb < 2; ++kb) {  // key half kb accumulates into its own O (own softmax reference)
@@ -410,7 +413,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_stream_kernel(const __grid_c
             ST_TRACE(0, n, 5);
             umma_commit(&s_full[rs_s.stage]);  // S(n+3) complete; without further slabs it still marks "PV(n) done"
           }
-          __syncwarp();
+          if (!ST_MMA_LANE0) __syncwarp();
           if (s_valid) s_advance();
           rs_s.advance(kSBufs);
           rv.advance(kVStages);
