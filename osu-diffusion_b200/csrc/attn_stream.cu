@@ -31,6 +31,7 @@
 //   warp 2        tcgen05.mma issuer (owns the TMEM allocation)
 //   warps 4-11    softmax: TMEM lane quadrant = warp % 4, key half = (warp - 4) / 4
 //   warps 12-15   epilogue: one thread per query row
+// (15 warps at 136 registers do not fit: registers are allocated to warps in groups of four.)
 // TMEM: S/P buffers 0-127, 128-255, 256-383 (slab n uses n % 3), O[half] 384 + 64 * half.
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -48,38 +49,10 @@ int make_tensor_map_3d(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t 
 
 namespace attn_st {
 
-#ifndef ST_DEFER
-#define ST_DEFER 0
-#endif
-#ifndef ST_EARLYPROBE
-#define ST_EARLYPROBE 1
-#endif
-// Sleep between probes of a barrier that is not complete yet (ns).  A polling loop costs issue slots and entries of
-// the memory-instruction queue on the scheduler it shares with two softmax warps; the producers and the epilogue
-// warps have a whole tile of slack, a softmax warp that has to wait for scores is AHEAD of its row partner.
-#ifndef ST_SLEEP_PROD
-#define ST_SLEEP_PROD 100
-#endif
-#ifndef ST_SLEEP_SOFT
-#define ST_SLEEP_SOFT 20
-#endif
-#ifndef ST_SLEEP_EPI
-#define ST_SLEEP_EPI 100
-#endif
-#ifndef ST_MMA_LANE0
-#define ST_MMA_LANE0 0
-#endif
-#ifndef ST_SKEW
-#define ST_SKEW 0
-#endif
-#ifndef ST_PWAIT
-#define ST_PWAIT 0
-#endif
+// Ablation builds (tools/build_variants.sh; wrong results, timing only): 1 = no MUFU, 2 = half the exponentials,
+// 3 = no softmax arithmetic at all (the floor of the pipeline around it).
 #ifndef ST_ABL
 #define ST_ABL 0
-#endif
-#ifndef ST_EPI_EARLY
-#define ST_EPI_EARLY 0
 #endif
 
 constexpr int kQ = 128;                      // queries per tile
@@ -95,6 +68,7 @@ constexpr int kSBufs = 3;                     // S/P buffers in TMEM: S runs kSB
 constexpr int kNumBars = 2 * kRing + 2 * kSBufs + 2 + 2 + 2;
 constexpr int kSmemBytes = kOffBar + kNumBars * 8 + 16;
 constexpr int kThreads = 16 * 32;
+constexpr int kSoftWarp0 = 4, kEpiWarp0 = 12;
 
 struct Params {
   CUtensorMap tma_qkv;  // 3-D: [3D cols, T, B], box [64, 128, 1]
@@ -265,12 +239,12 @@ __global__ void __launch_bounds__(kThreads, 1) attn_stream_kernel(const __grid_c
       Walk w;
       for (w.init(p, blockIdx.x); w.tile < p.total_tiles; w.next(p, G)) {
         const Tile t = w.get(p, true);
-        mbar_wait_sleep(&q_free[rq.stage], rq.phase ^ 1, ST_SLEEP_PROD);
+        mbar_wait_sleep(&q_free[rq.stage], rq.phase ^ 1, 200);
         mbar_expect_tx(&q_full[rq.stage], kTile);
         tma_load_3d(ring_q + rq.stage * kTile, &p.tma_qkv, &q_full[rq.stage], t.h * kHD, t.q0, t.b);
         rq.advance(kQStages);
         for (int j = 0; j < t.n_slabs; ++j) {
-          mbar_wait_sleep(&k_free[rk.stage], rk.phase ^ 1, ST_SLEEP_PROD);
+          mbar_wait_sleep(&k_free[rk.stage], rk.phase ^ 1, 200);
           mbar_expect_tx(&k_full[rk.stage], kTile);
           tma_load_3d(ring_k + rk.stage * kTile, &p.tma_qkv, &k_full[rk.stage], p.D + t.h * kHD,
                       (t.slab_lo + j) * kS, t.b);
@@ -286,7 +260,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_stream_kernel(const __grid_c
       for (w.init(p, blockIdx.x); w.tile < p.total_tiles; w.next(p, G)) {
         const Tile t = w.get(p, true);
         for (int j = 0; j < t.n_slabs; ++j) {
-          mbar_wait_sleep(&v_free[rv.stage], rv.phase ^ 1, ST_SLEEP_PROD);
+          mbar_wait_sleep(&v_free[rv.stage], rv.phase ^ 1, 200);
           mbar_expect_tx(&v_full[rv.stage], kTile);
           tma_load_3d(ring_v + rv.stage * kTile, &p.tma_qkv, &v_full[rv.stage], 2 * p.D + t.h * kHD,
                       (t.slab_lo + j) * kS, t.b);
@@ -304,10 +278,10 @@ __global__ void __launch_bounds__(kThreads, 1) attn_stream_kernel(const __grid_c
     // The WHOLE warp runs this loop converged and one elected lane issues: every operand of tcgen05.mma must sit in
     // a uniform register, and inside an `if (lane == 0)` region the compiler cannot prove that, so it wraps each MMA
     // in an ELECT / R2UR / BRA.U.ANY loop.
-    if (!ST_MMA_LANE0 || lane == 0) {
+    {
       constexpr uint32_t idesc_s = idesc(kS, false);
       constexpr uint32_t idesc_o = idesc(kHD, true);
-      const uint32_t tb = ST_MMA_LANE0 ? tmem_base : __shfl_sync(0xffffffffu, tmem_base, 0);  // provably warp-uniform
+      const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);  // provably warp-uniform
       const uint32_t sbase = smem_u32(smem);
       // descriptors of stage 0 of each ring; stage s adds s * (kTile >> 4) to the 14-bit address field (the whole
       // dynamic shared memory lies below 256 KB, so the field cannot carry)
@@ -352,13 +326,13 @@ __global__ void __launch_bounds__(kThreads, 1) attn_stream_kernel(const __grid_c
             if (j_s == 0) mbar_wait_sleep(&q_full[rq.stage], rq.phase, 20);
             mbar_wait_sleep(&k_full[rk.stage], rk.phase, 20);
           }
-          if (!ST_MMA_LANE0) __syncwarp();
+          __syncwarp();
           tc_fence_after();
-          if ((ST_MMA_LANE0 || elect_one())) {
+          if (elect_one()) {
             s_mmas();
             umma_commit(&s_full[rs_s.stage]);
           }
-          if (!ST_MMA_LANE0) __syncwarp();
+          __syncwarp();
           s_advance();
           rs_s.advance(kSBufs);
         }
@@ -375,17 +349,9 @@ __global__ void __launch_bounds__(kThreads, 1) attn_stream_kernel(const __grid_c
           const bool ok_k = !s_valid || probe(&k_full[rk.stage], rk.phase);
           const bool ok_q = !(s_valid && j_s == 0) || probe(&q_full[rq.stage], rq.phase);
           const bool ok_o = !(j == 0 && tn >= 1) || probe(o_free, (tn - 1) & 1);  // the epilogue has read the previous O
-#if ST_PWAIT == 2  // every lane probes: no divergent region around the wait
-          while (!mbar_try_wait(&p_full[rs.stage], rs.phase)) {
-          }
-#endif
           if (lane == 0) {
             ST_TRACE(0, n, 0);
-#if ST_PWAIT == 1
-            mbar_wait(&p_full[rs.stage], rs.phase);
-#elif ST_PWAIT == 0
             mbar_wait_sleep(&p_full[rs.stage], rs.phase, 20);
-#endif
             ST_TRACE(0, n, 1);
             ensure(ok_v, &v_full[rv.stage], rv.phase);
             ensure(ok_o, o_free, (tn - 1) & 1);
@@ -395,11 +361,11 @@ __global__ void __launch_bounds__(kThreads, 1) attn_stream_kernel(const __grid_c
             }
             ST_TRACE(0, n, 3);
           }
-          if (!ST_MMA_LANE0) __syncwarp();
+          __syncwarp();
           tc_fence_after();
           const uint64_t dv = dv0 + static_cast<uint32_t>(rv.stage) * kStageStep;
           const uint32_t pa = tb + rs.stage * kS;  // P(n): per key half 32 columns of packed bf16 pairs
-          if ((ST_MMA_LANE0 || elect_one())) {
+          if (elect_one()) {
             ST_TRACE(0, n, 4);
 #pragma unroll
             for (int kb = 0; kb < 2; ++kb) {  // key half kb accumulates into its own O (own softmax reference)
@@ -413,7 +379,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_stream_kernel(const __grid_c
             ST_TRACE(0, n, 5);
             umma_commit(&s_full[rs_s.stage]);  // S(n+3) complete; without further slabs it still marks "PV(n) done"
           }
-          if (!ST_MMA_LANE0) __syncwarp();
+          __syncwarp();
           if (s_valid) s_advance();
           rs_s.advance(kSBufs);
           rv.advance(kVStages);
@@ -422,12 +388,12 @@ __global__ void __launch_bounds__(kThreads, 1) attn_stream_kernel(const __grid_c
         }
       }
     }
-  } else if (warp >= 4 && warp < 12) {
+  } else if (warp >= kSoftWarp0 && warp < kEpiWarp0) {
     // ------------------------------------------------- softmax: two threads per query row (64 keys of the slab each)
-    const int half = (warp - 4) >> 2;
+    const int half = (warp - kSoftWarp0) >> 2;
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
-    const bool lead = warp == 4 && lane == 0;  // releases K / Q buffers
+    const bool lead = warp == kSoftWarp0 && lane == 0;  // releases K / Q / V buffers
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     float2* xchg = reinterpret_cast<float2*>(smem + kOffX);
     uint32_t n = 0, tn = 0;
@@ -436,14 +402,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_stream_kernel(const __grid_c
 
     // The scores of slab n+1 are fetched while slab n is still being exponentiated (its buffer is the other one and
     // S runs two slabs ahead), so the barrier probe and the TMEM read latency sit under the MUFU stream.
-#if ST_SKEW > 0
-    // The two threads of a row would otherwise run in lockstep (same barriers, same work): both in their MUFU phase,
-    // then both in the scalar part of the slab, with the XU pipe idle.  Half 1 starts late and stays late.
-    if (half == 1) __nanosleep(ST_SKEW);
-#endif
     uint32_t va[32], vb[32];
-    bool pending = false;  // P of the previous slab written but not yet published
-    Ring rs_pending;
     warp_mbar_wait_sleep(&s_full[0], 0, 20);
     tc_fence_after();
     constexpr uint32_t col_o_base = kSBufs * kS;
@@ -481,11 +440,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_stream_kernel(const __grid_c
         if (tracer) ST_TRACE(1 + half, n, 0);
         // probe S(n+1) now, use the answer after the first chunk: a barrier probe costs ~240 cycles even on success
         bool next_ready = true;
-#if ST_EARLYPROBE
         if (has_next && lane == 0) next_ready = mbar_try_wait(&s_full[rs_next.stage], rs_next.phase);
-#else
-        if (lane == 0) next_ready = false;
-#endif
         tmem_ld_wait();  // all 64 scores of slab n are in registers: their columns may be overwritten from here on
         if (tracer) ST_TRACE(1 + half, n, 2);
         if (lead) {  // S(n) is complete: its K stage (and, after the tile's last slab, Q) is free
@@ -585,22 +540,19 @@ __global__ void __launch_bounds__(kThreads, 1) attn_stream_kernel(const __grid_c
               if (redo) exps(-ref);
             }
             sum += csum;
-          } else {
+          } else {  // no row of this warp may attend these 32 keys: P = 0 (PV covers the whole slab)
+            uint32_t zero[16];
 #pragma unroll
-            for (int k = 0; k < 16; ++k) packed[k] = 0u;
-          }
-          if (c == 0 && pending) {  // publish P(n-1) now: its stores were issued a whole chunk ago, so the wait is free
-            tmem_st_wait();
-            tc_fence_before();
-            warp_mbar_arrive(&p_full[rs_pending.stage]);
-            pending = false;
+            for (int k = 0; k < 16; ++k) zero[k] = 0u;
+            tmem_st_32x16(t_s + c * 16, zero);
+            return;
           }
           tmem_st_32x16(t_s + c * 16, packed);
         };
         chunk(va, 0, live0);
         if (tracer) ST_TRACE(1 + half, n, 3);
         if (has_next) {  // slab n+1's scores, first chunk: va is free
-          if (!next_ready) mbar_wait_sleep(&s_full[rs_next.stage], rs_next.phase, ST_SLEEP_SOFT);  // lane 0 only
+          if (!next_ready) mbar_wait_sleep(&s_full[rs_next.stage], rs_next.phase, 20);  // lane 0 only
           if (lead && n >= 2) mbar_arrive(&v_free[rv_rel.stage]);  // S(n+1) complete => PV(n-2), issued before it, too
           __syncwarp();
           tc_fence_after();
@@ -626,15 +578,9 @@ __global__ void __launch_bounds__(kThreads, 1) attn_stream_kernel(const __grid_c
             tmem_st_32x32(t_lane + col_o + hh * 32, o);
           }
         }
-#if ST_DEFER
-        // P(n) (and a rescaled O_h) are published after the first chunk of the next slab, when the stores have landed
-        rs_pending = rs;
-        pending = true;
-#else
         tmem_st_wait();  // P(n) (and a rescaled O_h) are in tensor memory
         tc_fence_before();
         warp_mbar_arrive(&p_full[rs.stage]);
-#endif
         rs = rs_next;
         if (n >= 2) rv_rel.advance(kVStages);
         if (tracer) ST_TRACE(1 + half, n, 5);
@@ -645,12 +591,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_stream_kernel(const __grid_c
       xchg[((tn & 1) * 2 + half) * kQ + row] = make_float2(ref, sum);
       warp_mbar_arrive(&x_full[tn & 1]);
     }
-    if (pending) {
-      tmem_st_wait();
-      tc_fence_before();
-      warp_mbar_arrive(&p_full[rs_pending.stage]);
-    }
-  } else if (warp >= 12) {
+  } else if (warp >= kEpiWarp0) {
     // ---- epilogue: (w0 O0 + w1 O1) / (w0 s0 + w1 s1) -> bf16 -> global; log-sum-exp for the backward
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
@@ -665,11 +606,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_stream_kernel(const __grid_c
       // the previous tile's TMA store has read the staging tile (per-thread rows would touch 32 cache lines per
       // store instruction and hold the LSU for ~1 000 cycles per tile, which every mbarrier operation of the CTA
       // queues behind: tools/attn_stream_trace.py showed all roles stalling at tile boundaries)
-#if ST_EPI_EARLY
-      if (warp == 12 && lane == 0) tma_store_wait_read<0>();
-      named_bar_sync(1, 128);
-#endif
-      warp_mbar_wait_sleep(&x_full[tn & 1], par, ST_SLEEP_EPI);
+      warp_mbar_wait_sleep(&x_full[tn & 1], par, 100);
       const float2 ha = xchg[((tn & 1) * 2 + 0) * kQ + row];
       const float2 hb = xchg[((tn & 1) * 2 + 1) * kQ + row];
       warp_mbar_arrive(&x_free[tn & 1]);
@@ -682,10 +619,8 @@ __global__ void __launch_bounds__(kThreads, 1) attn_stream_kernel(const __grid_c
       constexpr uint32_t col_o = kSBufs * kS;
       warp_mbar_wait_sleep(o_full, tn & 1, 40);
       tc_fence_after();
-#if !ST_EPI_EARLY
-      if (warp == 12 && lane == 0) tma_store_wait_read<0>();
+      if (warp == kEpiWarp0 && lane == 0) tma_store_wait_read<0>();
       named_bar_sync(1, 128);
-#endif
       const uint32_t st_row = smem_u32(smem + kOffOut) + row * 128;
       const int swz = row & 7;
 #pragma unroll 1
@@ -707,14 +642,14 @@ __global__ void __launch_bounds__(kThreads, 1) attn_stream_kernel(const __grid_c
       }
       fence_proxy_async_smem();
       named_bar_sync(1, 128);
-      if (warp == 12 && lane == 0) {  // rows >= T are clipped by the tensor map
+      if (warp == kEpiWarp0 && lane == 0) {  // rows >= T are clipped by the tensor map
         tma_store_3d(&p.tma_out, smem + kOffOut, t.h * kHD, t.q0, t.b);
         tma_store_commit();
       }
       if (p.lse != nullptr && q < p.T)
         p.lse[(static_cast<int64_t>(t.b) * p.H + t.h) * p.T + q] = rmax + log2f(total);
     }
-    if (warp == 12 && lane == 0) tma_store_wait<0>();
+    if (warp == kEpiWarp0 && lane == 0) tma_store_wait<0>();
   }
 
   tc_fence_before();
