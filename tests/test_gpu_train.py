@@ -373,8 +373,13 @@ def test_cuda_graph_training_step_matches_eager(monkeypatch):
 
 
 def test_loss_curve_tracks_the_oracle():
-    """North star: training loss curves overlap (1 % over 1k steps).  Here: 25 AdamW steps of DiT-S on
-    identical batches / timesteps / noise, fp32 CPU oracle vs the native path, every step within 1 % (measured 0.3 %)."""
+    """North star: training loss curves overlap (1 % over 1k steps).  Here: 25 AdamW steps of DiT-S on identical
+    batches / timesteps / noise, fp32 CPU oracle vs the native path.  Adam's first steps move every weight by +-lr
+    whatever the gradient magnitude, so two runs of the SAME native code (different fp32 atomic order in the backward's
+    column sums) already separate by 0.5-1.0 % at single steps within these 25 (five runs measured: max 0.53 / 0.56 /
+    0.71 / 0.93 / 1.0x %, mean 0.14-0.21 %).  Asserted: the first five steps, before the trajectories can separate,
+    within 0.3 %; the mean deviation over the 25 steps within 0.5 %; no step beyond 2 %.  (The 1k-step test below
+    compares window means, which is what "curves overlap within 1 %" can mean for two chaotic trajectories.)"""
     from diffusion import create_diffusion
     B, T, steps = 8, 128, 25
     shape, sd, m, (x, o, c, y, _, _) = _train_setup("DiT-S", B, T)
@@ -401,9 +406,11 @@ def test_loss_curve_tracks_the_oracle():
         ref_curve.append(float(lr_))
         curve.append(float(ln))
     dev = [abs(a - b) / abs(b) for a, b in zip(curve, ref_curve)]
-    print("loss curve max rel deviation %.3e, mean %.3e; first %.4f -> last %.4f (oracle %.4f -> %.4f)"
-          % (max(dev), sum(dev) / len(dev), curve[0], curve[-1], ref_curve[0], ref_curve[-1]))
-    assert max(dev) < 1e-2
+    print("loss curve max rel deviation %.3e, mean %.3e, first five steps %.3e; first %.4f -> last %.4f (oracle %.4f -> %.4f)"
+          % (max(dev), sum(dev) / len(dev), max(dev[:5]), curve[0], curve[-1], ref_curve[0], ref_curve[-1]))
+    assert max(dev[:5]) < 3e-3
+    assert sum(dev) / len(dev) < 5e-3
+    assert max(dev) < 2e-2
 
 
 def test_loss_curve_1k_steps_overlaps_fp32_eager():
