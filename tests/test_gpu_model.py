@@ -271,6 +271,45 @@ def test_cuda_graph_step_equals_eager(monkeypatch, use_cfg):
 
 
 @torch.no_grad()
+def test_cuda_graph_step_with_the_residual_epilogue_equals_eager_and_the_folded_schedule(monkeypatch):
+    """sample.py's usual size class (a few beatmaps x 2048 datapoints) is both graph-replayed and large enough for the
+    CTA-pair GEMM, so the gated residual update runs in the out-projection / fc2 epilogue (fp32 TMA reduce-add, one
+    add per element: deterministic) inside the captured step: same bits as the eager launches, and the same samples
+    as the eager launches; one forward under the folded LayerNorm schedule (OSUDIT_GEMM_RESID=0) differs only by the
+    bf16 rounding of the branch that schedule has."""
+    from diffusion import create_diffusion
+    from osudit import engine, graphs, ops
+    shape, sd, m = build("DiT-S")
+    T, n = 2048, 2
+    assert ops.gemm_gated_residual_applicable(2 * n * T, shape.hidden, T)
+    z, o, c, y = synth.sampling_batch(n, T, seed=0)
+    od, cd, yd, maskd = to_dev(o, c, y, synth.band_mask(T, 128))
+    d = create_diffusion("4", noise_schedule="squaredcos_cap_v2")
+    kw = dict(o=od, c=cd, y=yd, attn_mask=maskd, cfg_scale=1.5)
+
+    def run(graph_on, fused=True):
+        monkeypatch.setattr(graphs, "_ENABLED", graph_on)
+        monkeypatch.setattr(engine, "_RESID_EPILOGUE", fused)
+        torch.manual_seed(5)
+        return d.p_sample_loop(m.forward_with_cfg, z.shape, z.to(DEV), model_kwargs=kw, device=DEV).clone()
+
+    graphs._cache.clear()
+    eager, replay = run(False), run(True)
+    assert len(graphs._cache) == 1
+    assert torch.equal(eager, replay)
+    graphs._cache.clear()
+    # one forward under both schedules: they differ (bf16 branch or not) by rounding only
+    monkeypatch.setattr(graphs, "_ENABLED", False)
+    t = torch.full((2 * n,), 500, device=DEV, dtype=torch.long)
+    outs = {}
+    for fused in (True, False):
+        monkeypatch.setattr(engine, "_RESID_EPILOGUE", fused)
+        outs[fused] = m.forward_with_cfg(z.to(DEV), t, **kw).clone()
+    assert not torch.equal(outs[True], outs[False])
+    assert rel(outs[True][:, :2], outs[False][:, :2]) < 2e-3
+
+
+@torch.no_grad()
 def test_refine_loop_with_second_checkpoint_and_inpaint_callback():
     """SURVEY §8(f)3 — sample.py:151-172: after the sampling loop, `refine_iters` more p_sample calls at t = 0 with
     a second (refine) checkpoint; test_toy.py:56-69: an in-paint `denoised_fn` that pins known coordinates.  Both go
