@@ -26,12 +26,35 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // NV = D / 128: float4 vectors per lane.
+// The read-only variant (no pending residual update) streams x once and h once: loads bypass L1 allocation, stores are
+// marked streaming.  Measured at config 2 (tools/resid_bench.py): 0.232 -> 0.205 ms after the out-projection, 0.231 ->
+// 0.227 ms after fc2.  LN_HINTS=0 builds the plain loads / stores.
+#ifndef LN_HINTS
+#define LN_HINTS 1
+#endif
+__device__ __forceinline__ float4 ld_stream(const float* p) {
+#if LN_HINTS
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+#else
+  return *reinterpret_cast<const float4*>(p);
+#endif
+}
+__device__ __forceinline__ void st_stream(__nv_bfloat16* p, uint2 v) {
+#if LN_HINTS
+  asm volatile("st.global.cs.v2.b32 [%0], {%1, %2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+#else
+  *reinterpret_cast<uint2*>(p) = v;
+#endif
+}
+
 template <int NV, bool kHasBranch>
 __device__ __forceinline__ void load_row_update(float4 (&v)[NV], float* __restrict__ xrow,
                                                 const __nv_bfloat16* __restrict__ yrow,
                                                 const float* __restrict__ gate, int lane) {
 #pragma unroll
-  for (int i = 0; i < NV; ++i) v[i] = *reinterpret_cast<const float4*>(xrow + (lane + 32 * i) * 4);
+  for (int i = 0; i < NV; ++i) v[i] = kHasBranch ? *reinterpret_cast<const float4*>(xrow + (lane + 32 * i) * 4) : ld_stream(xrow + (lane + 32 * i) * 4);
   if (kHasBranch) {
     uint2 yv[NV];
 #pragma unroll
@@ -103,7 +126,7 @@ ln_modulate_kernel(float* __restrict__ x, const __nv_bfloat16* __restrict__ y,
     uint2 o;
     o.x = pack_bf16(o0, o1);
     o.y = pack_bf16(o2, o3);
-    *reinterpret_cast<uint2*>(hrow + c) = o;
+    if (kHasBranch) *reinterpret_cast<uint2*>(hrow + c) = o; else st_stream(hrow + c, o);
   }
 }
 
