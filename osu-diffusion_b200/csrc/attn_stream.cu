@@ -1,18 +1,18 @@
-// Streaming self-attention on tcgen05, third schedule: ONE query tile per CTA at a time, every hand-off double-buffered,
-// softmax warps that never wait for the tensor pipe in steady state, and an instruction-lean exponentiation loop.
+// Streaming self-attention on tcgen05, third schedule: ONE query tile per CTA at a time, every hand-off buffered two or
+// three deep, softmax warps that do not wait for the tensor pipe in steady state, an instruction-lean exponentiation loop.
 //
 // Reference: nn.MultiheadAttention's core inside DiTBlock (models.py:164-170): per head
 // softmax(q k^T / sqrt(hd) + mask) v, under the band mask of sample.py:81-84 (query j sees key i iff
 // -w_left <= i - j <= w_right) or no mask (training windows, train.py:249-255).  head_dim 64.
 //
-// Why a third kernel (profiles/r02_summary.md, "attention: what bounds it"): on the sampling band the window kernel's
+// Why a third kernel (DESIGN.md section 4.2 [r2b], profiles/r02b_*): on the sampling band the window kernel's
 // softmax warps idle 47 % of the time (S is single-buffered: they wait for S(i+1) and for PV(i)), the two-slot kernel
 // (attn_fa.cu) hides those waits but issues 13.6 k warp instructions per tile, 9 per score, against the 8-cycle MUFU
 // cadence that is the real floor (16 exp2 per clock per SM, measured; TMEM reads run at 225 B/clk and are not a bound).
 // Here:
 //   * the CTA's slabs (128 keys each) form ONE sequence n = 0, 1, 2, ... across its tiles; S(n) lands in TMEM buffer
-//     n & 1 and is issued two slabs ahead (right after PV(n-2)); the output accumulators alternate per tile;
-//     Q / K / V travel through 3 / 5 / 5 stage rings;
+//     n % 3 and is issued three slabs ahead of PV (together with PV(n-3), whose P it overwrites: the tensor pipe runs in
+//     issue order), i.e. two slabs ahead of the softmax; Q / K / V travel through 3 / 4 / 5 stage rings;
 //   * P never touches shared memory: each softmax thread writes its bf16 probabilities back into the TMEM columns
 //     its scores came from (tcgen05.st) and PV takes its A operand from tensor memory.  With P in shared memory the
 //     kernel moved 150 KB per slab through the 128 B/clk shared-memory port (Q + K and P + V operand reads, the P
