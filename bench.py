@@ -50,11 +50,13 @@ def ncu_gemm_traffic():
         vals = []
         for line in open(path):
             cells = [c.strip() for c in line.strip().strip("|").split("|")]
-            if "dram bytes_read [Gbyte]" in line and "kernel" in cells[0]:
-                rd = next(i for i, c in enumerate(cells) if c.startswith("dram bytes_read"))
-                wr = next(i for i, c in enumerate(cells) if c.startswith("dram bytes_write"))
+            if "kernel" in cells[0] and ("dram bytes_read [Gbyte]" in line or "dram rd [Gbyte]" in line):
+                rd = next(i for i, c in enumerate(cells) if c.startswith(("dram bytes_read", "dram rd")))
+                wr = next(i for i, c in enumerate(cells) if c.startswith(("dram bytes_write", "dram wr")))
+                if "[Gbyte]" not in cells[wr]:  # mixed units in this table: not usable as is
+                    rd = wr = None
                 continue
-            if rd is not None and re.match(r"`gemm2_kernel<", cells[0]) and len(cells) > max(rd, wr):
+            if rd is not None and re.match(r"`(g2::)?gemm2_kernel<", cells[0]) and len(cells) > max(rd, wr):
                 try:
                     vals.append(float(cells[rd]) + float(cells[wr]))
                 except ValueError:
